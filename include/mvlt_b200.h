@@ -1,0 +1,103 @@
+/* mvlt_b200.h — C ABI of libmvlt_b200.so: hand-written sm_100a kernels for the MVLT multimodal forward hot path.
+ *
+ * The reference (Control-xl/Medical-Vision-Langauge-Transformer) has no FFI of its own: its boundary is the Python
+ * nn.Module surface.  Each entry point below replaces the ATen call sites named beside it; the
+ * Python host (medical_vision_langauge_transformer_b200/) keeps the reference's class names, forward signatures and
+ * state_dict keys and calls these through ctypes with raw device pointers.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every pointer is a DEVICE pointer unless noted;
+ * functions are stream-ordered on `stream`, allocate nothing, keep no global mutable state beyond one-time
+ * attribute setup, never throw or exit.  Return 0 on success, a negative MVLT_ERR_* for rejected arguments, or a
+ * positive cudaError_t.  dtype codes: 0 = fp32, 1 = bf16.  Row strides (ld*) are in ELEMENTS.
+ */
+#ifndef MVLT_B200_H_
+#define MVLT_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* mvlt_stream_t; /* == cudaStream_t */
+
+#define MVLT_OK 0
+#define MVLT_ERR_INVALID (-1)
+#define MVLT_ERR_UNSUPPORTED (-2)
+#define MVLT_ERR_DRIVER (-3)
+#define MVLT_F32 0
+#define MVLT_BF16 1
+#define MVLT_ACT_NONE 0
+#define MVLT_ACT_GELU 1 /* exact erf GELU (nn.GELU default), vfe.py:126, HF modeling_bert.py:336 */
+#define MVLT_ACT_TANH 2 /* BertPooler, HF modeling_bert.py:466 */
+
+/* One-time setup (driver entry points, opt-in shared memory sizes).  Call once per process after the CUDA
+ * context exists and before any stream capture.  Also reports the library ABI version. */
+int mvlt_init(void);
+int mvlt_abi_version(void);
+
+/* C[M,N] = act(A[M,K] . W[N,K]^T + bias) + residual — tcgen05/TMEM/TMA, bf16 operands, fp32 accumulate.
+ * Replaces nn.Linear at vfe.py:231 (qkv), :252 (proj), :136/:139 (fc1/fc2), :443 (reduction, bias=NULL) and
+ * HF modeling_bert.py:179-181 (Q|K|V packed as one [2304,768] weight), :295, :338, :352, :463, :476.
+ * A,W bf16; C fp32|bf16 (out_dtype); bias fp32 or NULL; residual fp32|bf16 (res_dtype) or NULL.
+ * K % 16 == 0, lda/ldw % 8 == 0.  block_n = 0 picks the tile width. */
+int mvlt_gemm_bf16_tc(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc,
+                      const float* bias, const void* residual, long long ldres, int res_dtype, int M, int N, int K,
+                      int act, int out_dtype, int block_n, mvlt_stream_t stream);
+
+/* Same contract in fp32 on the CUDA cores (parity mode, 1e-4 vs the reference). */
+int mvlt_gemm_f32_simt(const float* A, long long lda, const float* W, long long ldw, float* C, long long ldc,
+                       const float* bias, const float* residual, long long ldres, int M, int N, int K, int act,
+                       mvlt_stream_t stream);
+
+/* out[r,:] = LayerNorm(in[r,:]) * gamma + beta, optional erf-GELU after it.
+ * vfe.py:356,:385,:685 (+ model.py:232-235 GELU), HF modeling_bert.py:298,:356,:483. */
+int mvlt_layernorm_rows(const void* in, int in_dtype, long long ld_in, void* out, int out_dtype, long long ld_out,
+                        const float* gamma, const float* beta, long long rows, int C, float eps, int gelu,
+                        mvlt_stream_t stream);
+
+/* PatchEmbed: Conv2d(3,96,k=4,s=4) + LayerNorm(96); img fp32 NCHW [B,3,224,224] -> out fp32 [B,3136,96].
+ * vfe.py:557-565. */
+int mvlt_patch_embed_ln(const float* img, const float* weight, const float* bias, const float* gamma,
+                        const float* beta, float* out, int B, int img_size, int patch, int embed_dim, float eps,
+                        mvlt_stream_t stream);
+
+/* PatchMerging gather + LayerNorm(4C): x fp32 [B,H,W,C] -> out [B*H/2*W/2, 4C] in quad order (0,0),(1,0),(0,1),(1,1).
+ * vfe.py:433-442 (the Linear(4C,2C) that follows is mvlt_gemm_*). */
+int mvlt_patch_merge_ln(const float* x, void* out, int out_dtype, const float* gamma, const float* beta, int B, int H,
+                        int W, int C, float eps, mvlt_stream_t stream);
+
+/* Shifted-window attention with tokens in natural order: qkv [B*H*W, 3C] -> out [B*H*W, C]; the roll / partition /
+ * reverse of vfe.py:144-173,:361,:378 are folded into the row index map.  relbias fp32 [heads,64,64] = the gathered
+ * relative_position_bias (vfe.py:236-238), zero padded.  shift > 0 adds the -100 region mask of vfe.py:318-344. */
+int mvlt_window_attention(const void* qkv, void* out, int dtype, const float* relbias, int B, int H, int W, int C,
+                          int heads, int window, int shift, float scale, mvlt_stream_t stream);
+
+/* Joint embedding assembly + additive key mask: model.py:110-160, :162-183.
+ * feat [n_feat, n_obj, D]; img_index int32 [B] (row of feat per sample) or NULL for identity; ids int64 [B,L];
+ * text_mask / image_mask uint8 (image_mask may be NULL = all ones); word_emb fp32 [vocab+1, D];
+ * typepos fp32 [S, D] = token_type_emb[s <= n_obj+1] + position_emb[s]; out [B, S, D]; kmask fp32 [B,S]. */
+int mvlt_joint_embed(const void* feat, int feat_dtype, const int* img_index, const long long* ids,
+                     const unsigned char* text_mask, const unsigned char* image_mask, const float* word_emb,
+                     const float* typepos, void* out, int out_dtype, float* kmask, int B, int n_obj, int L, int D,
+                     int cls_id, int sep_id, mvlt_stream_t stream);
+
+/* BERT self-attention over the joint sequence: qkv [B*S, 3*heads*64] -> out [B*S, heads*64].
+ * HF modeling_bert.py:115-140; seq2seq != 0 applies the mask of model.py:118-123 instead of kmask. */
+int mvlt_joint_attention(const void* qkv, void* out, int dtype, const float* kmask, int B, int S, int heads,
+                         int head_dim, int seq2seq, int obj_end, float scale, mvlt_stream_t stream);
+
+/* out[r, n] = x[r,:] . w[n,:] + bias[n], N <= 16 (fp32 weights/outputs).  model.py:435, :363. */
+int mvlt_linear_small(const void* x, int x_dtype, long long ldx, const float* w, const float* bias, float* out,
+                      long long rows, int N, int K, mvlt_stream_t stream);
+
+/* Row softmax, fp32.  model.py:348, :468. */
+int mvlt_softmax_rows(const float* in, float* out, long long rows, int N, mvlt_stream_t stream);
+
+/* loss_sum[0] = sum over rows with label != ignore_index of (logsumexp(row) - row[label]); loss_sum[1] = their count.
+ * F.cross_entropy(..., ignore_index=-100) of model.py:410 and :418 (mean = [0]/[1]). */
+int mvlt_masked_ce_rows(const float* logits, long long ld, const long long* labels, float* loss_sum, long long rows,
+                        int N, long long ignore_index, mvlt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVLT_B200_H_ */

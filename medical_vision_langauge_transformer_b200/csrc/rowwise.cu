@@ -1,0 +1,278 @@
+// HBM-bound row kernels of the MVLT forward path: 128-bit vectorised loads/stores, one warp per row,
+// warp-shuffle reductions, the row held in registers (read once, write once).
+//
+//   mvlt_layernorm_rows      vfe.py:356,:385 (norm1/norm2), HF modeling_bert.py:298,:356 (post-LN, eps 1e-12),
+//                            vfe.py:685 + model.py:232-235 (final norm + GELU), HF :483 (head transform LN)
+//   mvlt_patch_embed_ln      vfe.py:557-565 (Conv2d k4 s4 as a 48->96 dot + LayerNorm(96))
+//   mvlt_patch_merge_ln      vfe.py:433-442 (2x2 gather in order (0,0),(1,0),(0,1),(1,1) + LayerNorm(4C))
+//   mvlt_joint_embed         model.py:110-160 + :162-183 ([CLS] img [SEP] text + type + position; additive key mask)
+#include "common.cuh"
+
+namespace mvlt {
+
+// One warp normalises one row of C elements (C % 4 == 0, C <= 128*NCH).  `src(c)` returns the 4 elements
+// starting at column c.  Two-pass statistics from registers (mean, then centred sum of squares).
+template <int NCH, typename TO, typename SrcFn>
+__device__ __forceinline__ void ln_row_core(SrcFn src, TO* __restrict__ dst, const float* __restrict__ gamma,
+                                            const float* __restrict__ beta, int C, float eps, bool gelu, int lane) {
+  float4 v[NCH];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    if (c < C) {
+      v[i] = src(c);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    if (c < C) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    if (c < C) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (gelu) {
+        o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w);
+      }
+      store4(dst + c, o);
+    }
+  }
+}
+
+template <int NCH, typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const TI* __restrict__ in, long long ld_in, TO* __restrict__ out, long long ld_out,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, int C, float eps,
+                      int gelu) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const TI* src = in + row * ld_in;
+  ln_row_core<NCH>([&](int c) { return load4(src + c); }, out + row * ld_out, gamma, beta, C, eps, gelu != 0,
+                   threadIdx.x & 31);
+}
+
+// out row (b, h2, w2) = LN( cat[x(2h2,2w2), x(2h2+1,2w2), x(2h2,2w2+1), x(2h2+1,2w2+1)] ), x fp32 [B,H,W,C]
+template <int NCH, typename TO>
+__global__ void __launch_bounds__(256)
+patch_merge_ln_kernel(const float* __restrict__ x, TO* __restrict__ out, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, int B, int H, int W, int C, float eps) {
+  const int H2 = H / 2, W2 = W / 2;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= (long long)B * H2 * W2) return;
+  const int w2 = (int)(row % W2), h2 = (int)((row / W2) % H2), b = (int)(row / ((long long)W2 * H2));
+  const float* base = x + (((long long)b * H + 2 * h2) * W + 2 * w2) * C;
+  ln_row_core<NCH>(
+      [&](int c) {
+        const int qd = c / C, within = c - qd * C;  // quarter: dh = qd & 1, dw = qd >> 1
+        return load4(base + ((long long)(qd & 1) * W + (qd >> 1)) * C + within);
+      },
+      out + row * 4LL * C, gamma, beta, 4 * C, eps, false, threadIdx.x & 31);
+}
+
+// One CTA per (image, patch row): 56 patches x 96 channels.  192 threads = 2 x 96: thread (half, c) keeps the 48
+// weights of channel c in registers and walks every other patch; LayerNorm(96) by one warp per patch afterwards.
+constexpr int PE_C = 96, PE_K = 48, PE_P = 56, PE_IMG = 224;
+__global__ void __launch_bounds__(192)
+patch_embed_ln_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
+                      float eps) {
+  __shared__ __align__(16) float in_s[3][4][PE_IMG];
+  __shared__ float out_s[PE_P][PE_C + 1];
+  const int b = blockIdx.x / PE_P, py = blockIdx.x % PE_P;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 3 * 4 * (PE_IMG / 4); i += 192) {
+    const int x4 = i % (PE_IMG / 4), ky = (i / (PE_IMG / 4)) % 4, ci = i / (4 * (PE_IMG / 4));
+    const float4 t = load4(img + (((long long)b * 3 + ci) * PE_IMG + (4 * py + ky)) * PE_IMG + 4 * x4);
+    *reinterpret_cast<float4*>(&in_s[ci][ky][4 * x4]) = t;
+  }
+  const int c = tid % PE_C, half = tid / PE_C;
+  float wr[PE_K];
+#pragma unroll
+  for (int k = 0; k < PE_K; k += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(w + c * PE_K + k));
+    wr[k] = t.x; wr[k + 1] = t.y; wr[k + 2] = t.z; wr[k + 3] = t.w;
+  }
+  const float bc = bias[c];
+  __syncthreads();
+  for (int p = half; p < PE_P; p += 2) {
+    float acc = bc;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) {
+        const float4 t = *reinterpret_cast<const float4*>(&in_s[ci][ky][4 * p]);
+        acc = fmaf(wr[ci * 16 + ky * 4 + 0], t.x, acc);
+        acc = fmaf(wr[ci * 16 + ky * 4 + 1], t.y, acc);
+        acc = fmaf(wr[ci * 16 + ky * 4 + 2], t.z, acc);
+        acc = fmaf(wr[ci * 16 + ky * 4 + 3], t.w, acc);
+      }
+    out_s[p][c] = acc;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int p = warp; p < PE_P; p += 6) {
+    const float v0 = out_s[p][lane], v1 = out_s[p][lane + 32], v2 = out_s[p][lane + 64];
+    const float mean = warp_sum(v0 + v1 + v2) * (1.0f / PE_C);
+    const float d0 = v0 - mean, d1 = v1 - mean, d2 = v2 - mean;
+    const float rstd = 1.0f / sqrtf(warp_sum(d0 * d0 + d1 * d1 + d2 * d2) * (1.0f / PE_C) + eps);
+    float* o = out + ((long long)b * (PE_P * PE_P) + py * PE_P + p) * PE_C;
+    o[lane] = d0 * rstd * gamma[lane] + beta[lane];
+    o[lane + 32] = d1 * rstd * gamma[lane + 32] + beta[lane + 32];
+    o[lane + 64] = d2 * rstd * gamma[lane + 64] + beta[lane + 64];
+  }
+}
+
+// One warp per joint-sequence row (b, s), D % 4 == 0, D <= 128*NCH.
+//   s in [1, n_obj]      : image feature row (already LN+GELU'd)          model.py:141
+//   s == 0 / n_obj+1     : word_emb[cls_id] / word_emb[sep_id]            model.py:133-136
+//   s >  n_obj+1         : word_emb[ids[b, s-n_obj-2]]                    model.py:138
+//   + typepos[s] = token_type_emb[s <= n_obj+1] + position_emb[s]         model.py:152-158 (precomputed table)
+// kmask[b,s] = 0 where attended, -10000 where masked (model.py:126,:182).
+template <int NCH, typename TF, typename TO>
+__global__ void __launch_bounds__(256)
+joint_embed_kernel(const TF* __restrict__ feat, const int* __restrict__ img_index, const long long* __restrict__ ids,
+                   const unsigned char* __restrict__ text_mask, const unsigned char* __restrict__ image_mask,
+                   const float* __restrict__ word_emb, const float* __restrict__ typepos, TO* __restrict__ out,
+                   float* __restrict__ kmask, int B, int n_obj, int L, int D, int cls_id, int sep_id) {
+  const int S = n_obj + 2 + L;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= (long long)B * S) return;
+  const int lane = threadIdx.x & 31;
+  const int b = (int)(row / S), s = (int)(row % S);
+  const float* tp = typepos + (long long)s * D;
+  TO* o = out + row * D;
+  bool keep = true;
+  if (s >= 1 && s <= n_obj) {
+    const int fi = img_index ? img_index[b] : b;
+    const TF* f = feat + ((long long)fi * n_obj + (s - 1)) * D;
+    if (image_mask) keep = image_mask[(long long)b * n_obj + (s - 1)] != 0;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      if (c < D) {
+        const float4 a = load4(f + c), t = __ldg(reinterpret_cast<const float4*>(tp + c));
+        store4(o + c, make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w));
+      }
+    }
+  } else {
+    long long id = cls_id;
+    if (s == n_obj + 1) id = sep_id;
+    else if (s > n_obj + 1) {
+      id = ids[(long long)b * L + (s - n_obj - 2)];
+      keep = text_mask[(long long)b * L + (s - n_obj - 2)] != 0;
+    }
+    const float* e = word_emb + id * D;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      if (c < D) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(e + c)), t = __ldg(reinterpret_cast<const float4*>(tp + c));
+        store4(o + c, make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w));
+      }
+    }
+  }
+  if (lane == 0) kmask[row] = keep ? 0.0f : -10000.0f;
+}
+
+template <typename TI, typename TO>
+static int launch_ln(const void* in, long long ld_in, void* out, long long ld_out, const float* gamma, const float* beta,
+                     long long rows, int C, float eps, int gelu, cudaStream_t st) {
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+#define LN_CASE(NCH)                                                                                              \
+  layernorm_rows_kernel<NCH, TI, TO><<<grid, 256, 0, st>>>((const TI*)in, ld_in, (TO*)out, ld_out, gamma, beta, \
+                                                           rows, C, eps, gelu)
+  if (C <= 128) LN_CASE(1);
+  else if (C <= 256) LN_CASE(2);
+  else if (C <= 384) LN_CASE(3);
+  else if (C <= 768) LN_CASE(6);
+  else if (C <= 1536) LN_CASE(12);
+  else if (C <= 3072) LN_CASE(24);
+  else return MVLT_ERR_UNSUPPORTED;
+#undef LN_CASE
+  return MVLT_OK;
+}
+
+}  // namespace mvlt
+
+using namespace mvlt;
+
+extern "C" int mvlt_layernorm_rows(const void* in, int in_dtype, long long ld_in, void* out, int out_dtype,
+                                   long long ld_out, const float* gamma, const float* beta, long long rows, int C,
+                                   float eps, int gelu, cudaStream_t stream) {
+  if (!in || !out || !gamma || !beta || rows <= 0 || C <= 0 || C % 4 || ld_in % 4 || ld_out % 4) return MVLT_ERR_INVALID;
+  int rc;
+  if (in_dtype == MVLT_F32 && out_dtype == MVLT_F32) rc = launch_ln<float, float>(in, ld_in, out, ld_out, gamma, beta, rows, C, eps, gelu, stream);
+  else if (in_dtype == MVLT_F32 && out_dtype == MVLT_BF16) rc = launch_ln<float, bf16>(in, ld_in, out, ld_out, gamma, beta, rows, C, eps, gelu, stream);
+  else if (in_dtype == MVLT_BF16 && out_dtype == MVLT_BF16) rc = launch_ln<bf16, bf16>(in, ld_in, out, ld_out, gamma, beta, rows, C, eps, gelu, stream);
+  else if (in_dtype == MVLT_BF16 && out_dtype == MVLT_F32) rc = launch_ln<bf16, float>(in, ld_in, out, ld_out, gamma, beta, rows, C, eps, gelu, stream);
+  else return MVLT_ERR_INVALID;
+  if (rc != MVLT_OK) return rc;
+  MVLT_LAUNCH_CHECK();
+  return MVLT_OK;
+}
+
+extern "C" int mvlt_patch_embed_ln(const float* img, const float* weight, const float* bias, const float* gamma,
+                                   const float* beta, float* out, int B, int img_size, int patch, int embed_dim,
+                                   float eps, cudaStream_t stream) {
+  if (!img || !weight || !bias || !gamma || !beta || !out || B <= 0) return MVLT_ERR_INVALID;
+  if (img_size != PE_IMG || patch != 4 || embed_dim != PE_C) return MVLT_ERR_UNSUPPORTED;  // Swin-S/T/B-224 patch stem
+  patch_embed_ln_kernel<<<B * PE_P, 192, 0, stream>>>(img, weight, bias, gamma, beta, out, eps);
+  MVLT_LAUNCH_CHECK();
+  return MVLT_OK;
+}
+
+extern "C" int mvlt_patch_merge_ln(const float* x, void* out, int out_dtype, const float* gamma, const float* beta,
+                                   int B, int H, int W, int C, float eps, cudaStream_t stream) {
+  if (!x || !out || !gamma || !beta || B <= 0 || H % 2 || W % 2 || C % 4) return MVLT_ERR_INVALID;
+  const long long rows = (long long)B * (H / 2) * (W / 2);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const int C4 = 4 * C;
+#define PM_CASE(NCH)                                                                                            \
+  do {                                                                                                          \
+    if (out_dtype == MVLT_F32) patch_merge_ln_kernel<NCH, float><<<grid, 256, 0, stream>>>(x, (float*)out, gamma, beta, B, H, W, C, eps); \
+    else patch_merge_ln_kernel<NCH, bf16><<<grid, 256, 0, stream>>>(x, (bf16*)out, gamma, beta, B, H, W, C, eps); \
+  } while (0)
+  if (out_dtype != MVLT_F32 && out_dtype != MVLT_BF16) return MVLT_ERR_INVALID;
+  if (C4 <= 384) PM_CASE(3);
+  else if (C4 <= 768) PM_CASE(6);
+  else if (C4 <= 1536) PM_CASE(12);
+  else if (C4 <= 3072) PM_CASE(24);
+  else return MVLT_ERR_UNSUPPORTED;
+#undef PM_CASE
+  MVLT_LAUNCH_CHECK();
+  return MVLT_OK;
+}
+
+extern "C" int mvlt_joint_embed(const void* feat, int feat_dtype, const int* img_index, const long long* ids,
+                                const unsigned char* text_mask, const unsigned char* image_mask, const float* word_emb,
+                                const float* typepos, void* out, int out_dtype, float* kmask, int B, int n_obj, int L,
+                                int D, int cls_id, int sep_id, cudaStream_t stream) {
+  if (!feat || !ids || !text_mask || !word_emb || !typepos || !out || !kmask || B <= 0 || n_obj <= 0 || L < 0) return MVLT_ERR_INVALID;
+  if (D != 768) return MVLT_ERR_UNSUPPORTED;
+  if (feat_dtype != out_dtype) return MVLT_ERR_INVALID;
+  const long long rows = (long long)B * (n_obj + 2 + L);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (out_dtype == MVLT_F32)
+    joint_embed_kernel<6, float, float><<<grid, 256, 0, stream>>>((const float*)feat, img_index, ids, text_mask, image_mask, word_emb, typepos, (float*)out, kmask, B, n_obj, L, D, cls_id, sep_id);
+  else if (out_dtype == MVLT_BF16)
+    joint_embed_kernel<6, bf16, bf16><<<grid, 256, 0, stream>>>((const bf16*)feat, img_index, ids, text_mask, image_mask, word_emb, typepos, (bf16*)out, kmask, B, n_obj, L, D, cls_id, sep_id);
+  else return MVLT_ERR_INVALID;
+  MVLT_LAUNCH_CHECK();
+  return MVLT_OK;
+}

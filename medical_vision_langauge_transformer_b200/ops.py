@@ -1,0 +1,192 @@
+"""Thin torch-tensor wrappers over the C ABI (raw `data_ptr()` + current CUDA stream).  PyTorch is used for device
+memory and streams only; every arithmetic op below runs in libmvlt_b200.so.  No fallbacks."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_GELU, ACT_TANH = 0, 1, 2
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _code(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype}") from None
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _rows2d(t: torch.Tensor):
+    """(rows, cols, ld) of a tensor viewed as a row-major matrix with unit inner stride."""
+    assert t.is_cuda and t.dim() >= 2 and t.stride(-1) == 1, "expected a CUDA tensor with contiguous last dim"
+    if t.dim() == 2:
+        return t.shape[0], t.shape[1], t.stride(0)
+    assert t.is_contiguous()
+    return t.numel() // t.shape[-1], t.shape[-1], t.shape[-1]
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+           out_dtype: Optional[torch.dtype] = None, block_n: int = 0) -> torch.Tensor:
+    """out = act(x @ w.T + bias) + residual.  bf16 x/w -> tcgen05 GEMM; fp32 x/w -> CUDA-core parity GEMM."""
+    lib = _lib.ensure_init()
+    M, K, lda = _rows2d(x)
+    N, Kw, ldw = _rows2d(w)
+    assert K == Kw, (x.shape, w.shape)
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=out_dtype or x.dtype)
+    Mo, No, ldc = _rows2d(out)
+    assert (Mo, No) == (M, N)
+    ldres = 0
+    if residual is not None:
+        Mr, Nr, ldres = _rows2d(residual)
+        assert (Mr, Nr) == (M, N)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
+    if x.dtype == torch.bfloat16:
+        assert w.dtype == torch.bfloat16
+        rc = lib.mvlt_gemm_bf16_tc(x.data_ptr(), lda, w.data_ptr(), ldw, out.data_ptr(), ldc, _ptr(bias), _ptr(residual),
+                                   ldres, -1 if residual is None else _code(residual), M, N, K, act, _code(out), block_n,
+                                   _stream())
+        _lib.check(rc, f"mvlt_gemm_bf16_tc(M={M},N={N},K={K})")
+    else:
+        assert x.dtype == w.dtype == out.dtype == torch.float32
+        assert residual is None or residual.dtype == torch.float32
+        rc = lib.mvlt_gemm_f32_simt(x.data_ptr(), lda, w.data_ptr(), ldw, out.data_ptr(), ldc, _ptr(bias), _ptr(residual),
+                                    ldres, M, N, K, act, _stream())
+        _lib.check(rc, f"mvlt_gemm_f32_simt(M={M},N={N},K={K})")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out_dtype: torch.dtype,
+              gelu: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.ensure_init()
+    rows, C, ld = _rows2d(x)
+    if out is None:
+        out = torch.empty((rows, C), device=x.device, dtype=out_dtype)
+    _, _, ldo = _rows2d(out)
+    rc = lib.mvlt_layernorm_rows(x.data_ptr(), _code(x), ld, out.data_ptr(), _code(out), ldo, gamma.data_ptr(),
+                                 beta.data_ptr(), rows, C, float(eps), int(gelu), _stream())
+    _lib.check(rc, "mvlt_layernorm_rows")
+    return out
+
+
+def patch_embed_ln(img: torch.Tensor, w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                   eps: float = 1e-5) -> torch.Tensor:
+    lib = _lib.ensure_init()
+    B = img.shape[0]
+    assert img.dtype == torch.float32 and img.is_contiguous() and w.is_contiguous()
+    E, P = w.shape[0], w.shape[-1]
+    n_tok = (img.shape[-1] // P) ** 2
+    out = torch.empty((B * n_tok, E), device=img.device, dtype=torch.float32)
+    rc = lib.mvlt_patch_embed_ln(img.data_ptr(), w.data_ptr(), b.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                 out.data_ptr(), B, img.shape[-1], P, E, float(eps), _stream())
+    _lib.check(rc, "mvlt_patch_embed_ln")
+    return out
+
+
+def patch_merge_ln(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, B: int, H: int, W: int, C: int,
+                   out_dtype: torch.dtype, eps: float = 1e-5) -> torch.Tensor:
+    lib = _lib.ensure_init()
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() == B * H * W * C
+    out = torch.empty((B * (H // 2) * (W // 2), 4 * C), device=x.device, dtype=out_dtype)
+    rc = lib.mvlt_patch_merge_ln(x.data_ptr(), out.data_ptr(), _code(out), gamma.data_ptr(), beta.data_ptr(), B, H, W, C,
+                                 float(eps), _stream())
+    _lib.check(rc, "mvlt_patch_merge_ln")
+    return out
+
+
+def window_attention(qkv: torch.Tensor, relbias: torch.Tensor, B: int, H: int, W: int, C: int, heads: int,
+                     window: int, shift: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.ensure_init()
+    assert qkv.is_contiguous() and qkv.shape == (B * H * W, 3 * C)
+    assert relbias.dtype == torch.float32 and relbias.shape == (heads, 64, 64) and relbias.is_contiguous()
+    if out is None:
+        out = torch.empty((B * H * W, C), device=qkv.device, dtype=qkv.dtype)
+    rc = lib.mvlt_window_attention(qkv.data_ptr(), out.data_ptr(), _code(qkv), relbias.data_ptr(), B, H, W, C, heads,
+                                   window, shift, float(scale), _stream())
+    _lib.check(rc, "mvlt_window_attention")
+    return out
+
+
+def joint_embed(feat: torch.Tensor, ids: torch.Tensor, text_mask: torch.Tensor, image_mask: Optional[torch.Tensor],
+                word_emb: torch.Tensor, typepos: torch.Tensor, cls_id: int, sep_id: int,
+                img_index: Optional[torch.Tensor] = None):
+    """-> (hidden [B*S, D] in feat.dtype, kmask fp32 [B, S])"""
+    lib = _lib.ensure_init()
+    B, L = ids.shape
+    n_obj, D = feat.shape[-2], feat.shape[-1]
+    S = n_obj + 2 + L
+    assert feat.is_contiguous() and ids.dtype == torch.int64 and ids.is_contiguous()
+    assert typepos.shape[0] >= S and typepos.dtype == torch.float32 and word_emb.dtype == torch.float32
+    tm = text_mask.to(torch.uint8).contiguous()
+    im = None if image_mask is None else image_mask.to(torch.uint8).contiguous()
+    if img_index is not None:
+        assert img_index.dtype == torch.int32 and img_index.numel() == B
+    else:
+        assert feat.shape[0] == B
+    out = torch.empty((B * S, D), device=feat.device, dtype=feat.dtype)
+    kmask = torch.empty((B, S), device=feat.device, dtype=torch.float32)
+    rc = lib.mvlt_joint_embed(feat.data_ptr(), _code(feat), _ptr(img_index), ids.data_ptr(), tm.data_ptr(), _ptr(im),
+                              word_emb.data_ptr(), typepos.data_ptr(), out.data_ptr(), _code(out), kmask.data_ptr(), B,
+                              n_obj, L, D, int(cls_id), int(sep_id), _stream())
+    _lib.check(rc, "mvlt_joint_embed")
+    return out, kmask
+
+
+def joint_attention(qkv: torch.Tensor, kmask: torch.Tensor, B: int, S: int, heads: int, seq2seq: bool, obj_end: int,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.ensure_init()
+    C = qkv.shape[1] // 3
+    hd = C // heads
+    assert qkv.is_contiguous() and qkv.shape[0] == B * S and kmask.shape == (B, S)
+    if out is None:
+        out = torch.empty((B * S, C), device=qkv.device, dtype=qkv.dtype)
+    rc = lib.mvlt_joint_attention(qkv.data_ptr(), out.data_ptr(), _code(qkv), kmask.data_ptr(), B, S, heads, hd,
+                                  int(seq2seq), obj_end, float(hd) ** -0.5, _stream())
+    _lib.check(rc, "mvlt_joint_attention")
+    return out
+
+
+def linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    lib = _lib.ensure_init()
+    rows, K, ld = _rows2d(x)
+    N = w.shape[0]
+    assert w.dtype == torch.float32 and w.is_contiguous() and w.shape[1] == K
+    out = torch.empty((rows, N), device=x.device, dtype=torch.float32)
+    rc = lib.mvlt_linear_small(x.data_ptr(), _code(x), ld, w.data_ptr(), _ptr(bias), out.data_ptr(), rows, N, K, _stream())
+    _lib.check(rc, "mvlt_linear_small")
+    return out
+
+
+def softmax_rows(x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.ensure_init()
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    out = torch.empty_like(x)
+    rc = lib.mvlt_softmax_rows(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _stream())
+    _lib.check(rc, "mvlt_softmax_rows")
+    return out
+
+
+def masked_ce(logits: torch.Tensor, labels: torch.Tensor, n_classes: int, ignore_index: int = -100) -> torch.Tensor:
+    """-> fp32 [2]: (sum of per-row losses over rows with label != ignore_index, number of such rows)."""
+    lib = _lib.ensure_init()
+    rows, _, ld = _rows2d(logits)
+    assert logits.dtype == torch.float32 and labels.dtype == torch.int64 and labels.numel() == rows
+    acc = torch.empty(2, device=logits.device, dtype=torch.float32)
+    rc = lib.mvlt_masked_ce_rows(logits.data_ptr(), ld, labels.contiguous().data_ptr(), acc.data_ptr(), rows, n_classes,
+                                 ignore_index, _stream())
+    _lib.check(rc, "mvlt_masked_ce_rows")
+    return acc

@@ -1,0 +1,233 @@
+"""Per-kernel parity on the GPU: every C-ABI entry point against a plain torch fp32 restatement of the same op
+(the oracle's functions where one exists).  Tolerances: fp32 kernels 1e-4 relative to the output scale,
+bf16 kernels 1e-2 (BASELINE.json north_star)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def rnd(*shape, seed=0, scale=1.0, device="cuda"):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(device)
+
+
+GEMM_SHAPES = [
+    # (M, N, K)  — the real call sites at small batch + ragged edges
+    (128, 128, 64), (256, 256, 128), (3136 * 2, 288, 96), (3136 * 2, 96, 96), (3136 * 2, 384, 96), (3136 * 2, 96, 384),
+    (784 * 2, 576, 192), (784 * 2, 192, 768), (196 * 2, 1152, 384), (196 * 2, 384, 1536), (98, 2304, 768),
+    (98, 768, 3072), (262, 2304, 768), (262, 3072, 768), (262, 768, 3072), (1568, 192, 384), (64, 224, 768),
+    (3, 768, 768), (160, 30522, 768), (1000, 160, 80),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_tc_plain(cuda, M, N, K):
+    from medical_vision_langauge_transformer_b200 import ops
+    a = rnd(M, K, seed=1).bfloat16()
+    w = rnd(N, K, seed=2, scale=1 / math.sqrt(K)).bfloat16()
+    ldc = (N + 31) // 32 * 32
+    out_full = torch.zeros(M, ldc, device="cuda", dtype=torch.float32)
+    out = out_full[:, :N]
+    ops.linear(a, w, out=out)
+    ref = a.float() @ w.float().t()
+    assert relerr(out, ref) < 2e-3, (M, N, K)
+    assert out_full[:, N:].abs().max().item() == 0 if ldc > N else True
+
+
+@pytest.mark.parametrize("block_n", [32, 64, 96, 128, 192, 256])
+def test_gemm_tc_block_n(cuda, block_n):
+    from medical_vision_langauge_transformer_b200 import ops
+    M, N, K = 777, 1152, 384
+    a = rnd(M, K, seed=3).bfloat16()
+    w = rnd(N, K, seed=4, scale=1 / math.sqrt(K)).bfloat16()
+    out = ops.linear(a, w, out_dtype=torch.float32, block_n=block_n)
+    assert relerr(out, a.float() @ w.float().t()) < 2e-3
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+@pytest.mark.parametrize("res", [None, torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_gemm_tc_epilogues(cuda, act, res, out_dtype):
+    from medical_vision_langauge_transformer_b200 import ops
+    M, N, K = 1000, 768, 384
+    a = rnd(M, K, seed=5).bfloat16()
+    w = rnd(N, K, seed=6, scale=1 / math.sqrt(K)).bfloat16()
+    bias = rnd(N, seed=7)
+    r = None if res is None else rnd(M, N, seed=8).to(res)
+    out = ops.linear(a, w, bias, act=act, residual=r, out_dtype=out_dtype)
+    ref = a.float() @ w.float().t() + bias
+    ref = F.gelu(ref) if act == 1 else torch.tanh(ref) if act == 2 else ref
+    if r is not None:
+        ref = ref + r.float()
+    assert relerr(out, ref) < (1e-2 if out_dtype == torch.bfloat16 else 2e-3)
+
+
+def test_gemm_tc_inplace_residual_and_strided_a(cuda):
+    from medical_vision_langauge_transformer_b200 import ops
+    # residual == out (Swin proj/fc2), and A = hidden[:, 0] with row stride S*D (pooler)
+    M, N, K = 512, 384, 384
+    a = rnd(M, K, seed=9).bfloat16()
+    w = rnd(N, K, seed=10, scale=0.05).bfloat16()
+    x = rnd(M, N, seed=11)
+    ref = x + a.float() @ w.float().t()
+    ops.linear(a, w, residual=x, out=x)
+    assert relerr(x, ref) < 2e-3
+    h = rnd(7, 131, 768, seed=12).bfloat16()
+    wp = rnd(768, 768, seed=13, scale=0.03).bfloat16()
+    out = ops.linear(h[:, 0], wp, rnd(768, seed=14), act=2, out_dtype=torch.float32)
+    ref = torch.tanh(h[:, 0].float() @ wp.float().t() + rnd(768, seed=14))
+    assert relerr(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(130, 100, 48), (262, 2304, 768), (1000, 96, 384), (64, 224, 768)])
+def test_gemm_simt(cuda, M, N, K):
+    from medical_vision_langauge_transformer_b200 import ops
+    a, w, b, r = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=1 / math.sqrt(K)), rnd(N, seed=3), rnd(M, N, seed=4)
+    out = ops.linear(a, w, b, act=1, residual=r)
+    ref = F.gelu(a.double() @ w.double().t() + b.double()) + r.double()
+    assert relerr(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("C", [96, 192, 384, 768, 1536])
+@pytest.mark.parametrize("dt_in,dt_out", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                          (torch.bfloat16, torch.bfloat16)])
+def test_layernorm(cuda, C, dt_in, dt_out):
+    from medical_vision_langauge_transformer_b200 import ops
+    x = (rnd(1003, C, seed=C) * 3 + 0.5).to(dt_in)
+    g, b = 1 + rnd(C, seed=1, scale=0.1), rnd(C, seed=2, scale=0.1)
+    for eps, gelu in ((1e-5, False), (1e-12, False), (1e-5, True)):
+        out = ops.layernorm(x, g, b, eps, dt_out, gelu=gelu)
+        ref = F.layer_norm(x.float(), (C,), g, b, eps)
+        ref = F.gelu(ref) if gelu else ref
+        assert relerr(out, ref) < (1e-2 if dt_out == torch.bfloat16 else 2e-6)
+
+
+def test_layernorm_tiny_variance_eps(cuda):
+    """patch-embed outputs of RGC-shaped images have variance ~ eps: eps must be honoured exactly."""
+    from medical_vision_langauge_transformer_b200 import ops
+    x = rnd(64, 96, seed=5, scale=2e-3)
+    g, b = torch.ones(96, device="cuda"), torch.zeros(96, device="cuda")
+    assert relerr(ops.layernorm(x, g, b, 1e-5, torch.float32), F.layer_norm(x, (96,), g, b, 1e-5)) < 2e-6
+
+
+def test_patch_embed(cuda):
+    from medical_vision_langauge_transformer_b200 import ops
+    from oracle import mvlt_oracle as O
+    for scale in (1.0, 0.02):
+        img = rnd(3, 3, 224, 224, seed=1, scale=scale)
+        sd = {"proj.weight": rnd(96, 3, 4, 4, seed=2, scale=0.1), "proj.bias": rnd(96, seed=3, scale=0.02),
+              "norm.weight": 1 + rnd(96, seed=4, scale=0.1), "norm.bias": rnd(96, seed=5, scale=0.05)}
+        out = ops.patch_embed_ln(img, sd["proj.weight"], sd["proj.bias"], sd["norm.weight"], sd["norm.bias"])
+        ref = O.patch_embed({k: v.cpu() for k, v in sd.items()}, "", img.cpu())
+        assert relerr(out.view(3, 3136, 96).cpu(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("H,C", [(56, 96), (28, 192), (14, 384)])
+def test_patch_merge(cuda, H, C):
+    from medical_vision_langauge_transformer_b200 import ops
+    from oracle import mvlt_oracle as O
+    B = 2
+    x = rnd(B, H * H, C, seed=H)
+    sd = {"norm.weight": 1 + rnd(4 * C, seed=1, scale=0.1), "norm.bias": rnd(4 * C, seed=2, scale=0.05),
+          "reduction.weight": rnd(2 * C, 4 * C, seed=3, scale=0.02)}
+    ref = O.patch_merging({k: v.cpu() for k, v in sd.items()}, "", x.cpu(), H, H)
+    a = ops.patch_merge_ln(x.view(-1, C), sd["norm.weight"], sd["norm.bias"], B, H, H, C, torch.float32)
+    out = ops.linear(a, sd["reduction.weight"])
+    assert relerr(out.view(B, -1, 2 * C).cpu(), ref) < 1e-5
+    a16 = ops.patch_merge_ln(x.view(-1, C), sd["norm.weight"], sd["norm.bias"], B, H, H, C, torch.bfloat16)
+    assert relerr(a16, a) < 1e-2
+
+
+def _window_case(H, C, heads, shift, seed):
+    from oracle import mvlt_oracle as O
+    B, ws = 2, 7
+    qkv = rnd(B * H * H, 3 * C, seed=seed)
+    table = rnd(169, heads, seed=seed + 1, scale=0.5)
+    # oracle restatement of vfe.py:231-251 given the qkv activations (natural token order)
+    x = qkv.cpu().view(B, H, H, 3 * C)
+    if shift:
+        x = torch.roll(x, (-shift, -shift), (1, 2))
+    xw = O.window_partition(x, ws)                              # [B*nW, 49, 3C]
+    q, k, v = xw.view(-1, 49, 3, heads, 32).permute(2, 0, 3, 1, 4)
+    attn = (q * 32 ** -0.5) @ k.transpose(-2, -1)
+    bias = table.cpu()[O.relative_position_index(ws).reshape(-1)].view(49, 49, heads).permute(2, 0, 1)
+    attn = attn + bias[None]
+    if shift:
+        m = O.shift_attn_mask(H, H, ws, shift)
+        nW = m.shape[0]
+        attn = (attn.view(B, nW, heads, 49, 49) + m[None, :, None]).view(-1, heads, 49, 49)
+    o = (attn.softmax(-1) @ v).transpose(1, 2).reshape(-1, 49, C)
+    o = O.window_reverse(o, ws, H, H)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    relb = torch.zeros(heads, 64, 64)
+    relb[:, :49, :49] = bias
+    return B, qkv, relb.cuda(), o.reshape(B * H * H, C)
+
+
+@pytest.mark.parametrize("H,C,heads", [(56, 96, 3), (28, 192, 6), (14, 384, 12), (7, 768, 24)])
+@pytest.mark.parametrize("shift", [0, 3])
+def test_window_attention(cuda, H, C, heads, shift):
+    from medical_vision_langauge_transformer_b200 import ops
+    if H == 7 and shift:
+        pytest.skip("stage 3 never shifts (vfe.py:302-305)")
+    B, qkv, relb, ref = _window_case(H, C, heads, shift, seed=H + shift)
+    out = ops.window_attention(qkv, relb, B, H, H, C, heads, 7, shift, 32 ** -0.5)
+    assert relerr(out.cpu(), ref) < 1e-5
+    out16 = ops.window_attention(qkv.bfloat16(), relb, B, H, H, C, heads, 7, shift, 32 ** -0.5)
+    assert relerr(out16.cpu(), ref) < 1.5e-2
+
+
+@pytest.mark.parametrize("L", [80, 23, 30, 1])
+@pytest.mark.parametrize("seq2seq", [False, True])
+def test_joint_embed_and_attention(cuda, L, seq2seq):
+    from medical_vision_langauge_transformer_b200 import ops, synth
+    from oracle import mvlt_oracle as O
+    B, D, heads = 3, 768, 12
+    S = 51 + L
+    feat = rnd(B, 49, D, seed=1)
+    ids = synth.synth_token_ids(B, L, seed=2, min_len=1).cuda()
+    sd = {"MVLBert.word_embeddings.weight": rnd(30523, D, seed=3), "MVLBert.position_embeddings.weight": rnd(512, D, seed=4),
+          "MVLBert.token_type_embeddings.weight": rnd(3, D, seed=5)}
+    pos = torch.arange(S, device="cuda")
+    typepos = sd["MVLBert.token_type_embeddings.weight"][(pos <= 50).long()] + sd["MVLBert.position_embeddings.weight"][pos]
+    h, kmask = ops.joint_embed(feat, ids, ids > 0, None, sd["MVLBert.word_embeddings.weight"], typepos.contiguous(), 101, 102)
+    ref_h = O.joint_embedding({k: v.cpu() for k, v in sd.items()}, ids.cpu(), feat.cpu())
+    assert relerr(h.view(B, S, D).cpu(), ref_h) < 1e-6
+    ref_mask = O.joint_attention_mask(ids.cpu(), 49, False)[:, 0, 0]
+    assert torch.equal(kmask.cpu(), ref_mask)
+    # attention on random qkv
+    qkv = rnd(B * S, 3 * D, seed=6)
+    q, k, v = qkv.cpu().view(B, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    mask = O.joint_attention_mask(ids.cpu(), 49, seq2seq)
+    ref = (((q @ k.transpose(2, 3)) * 0.125 + mask).softmax(-1) @ v).transpose(1, 2).reshape(B * S, D)
+    out = ops.joint_attention(qkv, kmask, B, S, heads, seq2seq, 50)
+    assert relerr(out.cpu(), ref) < 1e-5
+    out16 = ops.joint_attention(qkv.bfloat16(), kmask, B, S, heads, seq2seq, 50)
+    assert relerr(out16.cpu(), ref) < 1.5e-2
+
+
+def test_heads(cuda):
+    from medical_vision_langauge_transformer_b200 import ops
+    x = rnd(37, 768, seed=1)
+    w, b = rnd(2, 768, seed=2, scale=0.05), rnd(2, seed=3)
+    ref = x @ w.t() + b
+    assert relerr(ops.linear_small(x, w, b), ref) < 1e-5
+    assert relerr(ops.linear_small(x.bfloat16(), w, b), ref) < 1e-2
+    lg = rnd(37, 224, seed=4, scale=3)
+    assert relerr(ops.softmax_rows(lg), lg.softmax(-1)) < 1e-5
+    labels = torch.randint(0, 224, (37,), device="cuda")
+    labels[::3] = -100
+    acc = ops.masked_ce(lg, labels, 224)
+    ref = F.cross_entropy(lg, labels, ignore_index=-100, reduction="sum")
+    assert abs(acc[0].item() - ref.item()) < 1e-3 * abs(ref.item())
+    assert acc[1].item() == (labels != -100).sum().item()
