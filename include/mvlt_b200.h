@@ -48,11 +48,12 @@ int mvlt_gemm_f32_simt(const float* A, long long lda, const float* W, long long 
                        const float* bias, const float* residual, long long ldres, int M, int N, int K, int act,
                        mvlt_stream_t stream);
 
-/* out[r,:] = LayerNorm(in[r,:]) * gamma + beta, optional erf-GELU after it.
+/* out[r,:] = LayerNorm(in[r,:]) * gamma + beta, optional erf-GELU after it.  out_bf16_copy (or NULL) receives the
+ * same rows rounded to bf16: `out` fp32 stays the residual, the copy is the next GEMM's A operand.
  * vfe.py:356,:385,:685 (+ model.py:232-235 GELU), HF modeling_bert.py:298,:356,:483. */
 int mvlt_layernorm_rows(const void* in, int in_dtype, long long ld_in, void* out, int out_dtype, long long ld_out,
                         const float* gamma, const float* beta, long long rows, int C, float eps, int gelu,
-                        mvlt_stream_t stream);
+                        void* out_bf16_copy, long long ld_copy, mvlt_stream_t stream);
 
 /* PatchEmbed: Conv2d(3,96,k=4,s=4) + LayerNorm(96); img fp32 NCHW [B,3,224,224] -> out fp32 [B,3136,96].
  * vfe.py:557-565. */
@@ -73,12 +74,14 @@ int mvlt_window_attention(const void* qkv, void* out, int dtype, const float* re
 
 /* Joint embedding assembly + additive key mask: model.py:110-160, :162-183.
  * feat [n_feat, n_obj, D]; img_index int32 [B] (row of feat per sample) or NULL for identity; ids int64 [B,L];
- * text_mask / image_mask uint8 (image_mask may be NULL = all ones); word_emb fp32 [vocab+1, D];
- * typepos fp32 [S, D] = token_type_emb[s <= n_obj+1] + position_emb[s]; out [B, S, D]; kmask fp32 [B,S]. */
+ * text_mask uint8 [B,L] or NULL (= ids > 0, model.py:337); image_mask uint8 [B,n_obj] or NULL (= all ones);
+ * word_emb fp32 [vocab+1, D];
+ * typepos fp32 [S, D] = token_type_emb[s <= n_obj+1] + position_emb[s]; out [B, S, D]; out_bf16_copy as in
+ * mvlt_layernorm_rows (or NULL); kmask fp32 [B,S]. */
 int mvlt_joint_embed(const void* feat, int feat_dtype, const int* img_index, const long long* ids,
                      const unsigned char* text_mask, const unsigned char* image_mask, const float* word_emb,
-                     const float* typepos, void* out, int out_dtype, float* kmask, int B, int n_obj, int L, int D,
-                     int cls_id, int sep_id, mvlt_stream_t stream);
+                     const float* typepos, void* out, int out_dtype, void* out_bf16_copy, float* kmask, int B, int n_obj,
+                     int L, int D, int cls_id, int sep_id, mvlt_stream_t stream);
 
 /* BERT self-attention over the joint sequence: qkv [B*S, 3*heads*64] -> out [B*S, heads*64].
  * HF modeling_bert.py:115-140; seq2seq != 0 applies the mask of model.py:118-123 instead of kmask. */

@@ -14,7 +14,8 @@ namespace mvlt {
 // starting at column c.  Two-pass statistics from registers (mean, then centred sum of squares).
 template <int NCH, typename TO, typename SrcFn>
 __device__ __forceinline__ void ln_row_core(SrcFn src, TO* __restrict__ dst, const float* __restrict__ gamma,
-                                            const float* __restrict__ beta, int C, float eps, bool gelu, int lane) {
+                                            const float* __restrict__ beta, int C, float eps, bool gelu, int lane,
+                                            bf16* __restrict__ dst_copy = nullptr) {
   float4 v[NCH];
   float s = 0.f;
 #pragma unroll
@@ -51,6 +52,7 @@ __device__ __forceinline__ void ln_row_core(SrcFn src, TO* __restrict__ dst, con
         o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w);
       }
       store4(dst + c, o);
+      if (dst_copy) store4(dst_copy + c, o);  // bf16 shadow = next GEMM's A operand; `dst` stays the fp32 residual
     }
   }
 }
@@ -59,12 +61,12 @@ template <int NCH, typename TI, typename TO>
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const TI* __restrict__ in, long long ld_in, TO* __restrict__ out, long long ld_out,
                       const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, int C, float eps,
-                      int gelu) {
+                      int gelu, bf16* __restrict__ out_copy, long long ld_copy) {
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const TI* src = in + row * ld_in;
   ln_row_core<NCH>([&](int c) { return load4(src + c); }, out + row * ld_out, gamma, beta, C, eps, gelu != 0,
-                   threadIdx.x & 31);
+                   threadIdx.x & 31, out_copy ? out_copy + row * ld_copy : nullptr);
 }
 
 // out row (b, h2, w2) = LN( cat[x(2h2,2w2), x(2h2+1,2w2), x(2h2,2w2+1), x(2h2+1,2w2+1)] ), x fp32 [B,H,W,C]
@@ -149,7 +151,8 @@ __global__ void __launch_bounds__(256)
 joint_embed_kernel(const TF* __restrict__ feat, const int* __restrict__ img_index, const long long* __restrict__ ids,
                    const unsigned char* __restrict__ text_mask, const unsigned char* __restrict__ image_mask,
                    const float* __restrict__ word_emb, const float* __restrict__ typepos, TO* __restrict__ out,
-                   float* __restrict__ kmask, int B, int n_obj, int L, int D, int cls_id, int sep_id) {
+                   bf16* __restrict__ out_copy, float* __restrict__ kmask, int B, int n_obj, int L, int D, int cls_id,
+                   int sep_id) {
   const int S = n_obj + 2 + L;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= (long long)B * S) return;
@@ -157,6 +160,7 @@ joint_embed_kernel(const TF* __restrict__ feat, const int* __restrict__ img_inde
   const int b = (int)(row / S), s = (int)(row % S);
   const float* tp = typepos + (long long)s * D;
   TO* o = out + row * D;
+  bf16* o2 = out_copy ? out_copy + row * D : nullptr;
   bool keep = true;
   if (s >= 1 && s <= n_obj) {
     const int fi = img_index ? img_index[b] : b;
@@ -167,7 +171,9 @@ joint_embed_kernel(const TF* __restrict__ feat, const int* __restrict__ img_inde
       const int c = (lane + 32 * i) * 4;
       if (c < D) {
         const float4 a = load4(f + c), t = __ldg(reinterpret_cast<const float4*>(tp + c));
-        store4(o + c, make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w));
+        const float4 r = make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w);
+        store4(o + c, r);
+        if (o2) store4(o2 + c, r);
       }
     }
   } else {
@@ -175,7 +181,7 @@ joint_embed_kernel(const TF* __restrict__ feat, const int* __restrict__ img_inde
     if (s == n_obj + 1) id = sep_id;
     else if (s > n_obj + 1) {
       id = ids[(long long)b * L + (s - n_obj - 2)];
-      keep = text_mask[(long long)b * L + (s - n_obj - 2)] != 0;
+      keep = text_mask ? text_mask[(long long)b * L + (s - n_obj - 2)] != 0 : id > 0;  // model.py:337 (ids > 0)
     }
     const float* e = word_emb + id * D;
 #pragma unroll
@@ -183,7 +189,9 @@ joint_embed_kernel(const TF* __restrict__ feat, const int* __restrict__ img_inde
       const int c = (lane + 32 * i) * 4;
       if (c < D) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(e + c)), t = __ldg(reinterpret_cast<const float4*>(tp + c));
-        store4(o + c, make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w));
+        const float4 r = make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w);
+        store4(o + c, r);
+        if (o2) store4(o2 + c, r);
       }
     }
   }
@@ -192,11 +200,11 @@ joint_embed_kernel(const TF* __restrict__ feat, const int* __restrict__ img_inde
 
 template <typename TI, typename TO>
 static int launch_ln(const void* in, long long ld_in, void* out, long long ld_out, const float* gamma, const float* beta,
-                     long long rows, int C, float eps, int gelu, cudaStream_t st) {
+                     long long rows, int C, float eps, int gelu, void* out_copy, long long ld_copy, cudaStream_t st) {
   const unsigned grid = (unsigned)((rows + 7) / 8);
 #define LN_CASE(NCH)                                                                                              \
   layernorm_rows_kernel<NCH, TI, TO><<<grid, 256, 0, st>>>((const TI*)in, ld_in, (TO*)out, ld_out, gamma, beta, \
-                                                           rows, C, eps, gelu)
+                                                           rows, C, eps, gelu, (bf16*)out_copy, ld_copy)
   if (C <= 128) LN_CASE(1);
   else if (C <= 256) LN_CASE(2);
   else if (C <= 384) LN_CASE(3);
@@ -214,13 +222,14 @@ using namespace mvlt;
 
 extern "C" int mvlt_layernorm_rows(const void* in, int in_dtype, long long ld_in, void* out, int out_dtype,
                                    long long ld_out, const float* gamma, const float* beta, long long rows, int C,
-                                   float eps, int gelu, cudaStream_t stream) {
+                                   float eps, int gelu, void* out_bf16_copy, long long ld_copy, cudaStream_t stream) {
   if (!in || !out || !gamma || !beta || rows <= 0 || C <= 0 || C % 4 || ld_in % 4 || ld_out % 4) return MVLT_ERR_INVALID;
+  if (out_bf16_copy && ld_copy % 4) return MVLT_ERR_INVALID;
   int rc;
-  if (in_dtype == MVLT_F32 && out_dtype == MVLT_F32) rc = launch_ln<float, float>(in, ld_in, out, ld_out, gamma, beta, rows, C, eps, gelu, stream);
-  else if (in_dtype == MVLT_F32 && out_dtype == MVLT_BF16) rc = launch_ln<float, bf16>(in, ld_in, out, ld_out, gamma, beta, rows, C, eps, gelu, stream);
-  else if (in_dtype == MVLT_BF16 && out_dtype == MVLT_BF16) rc = launch_ln<bf16, bf16>(in, ld_in, out, ld_out, gamma, beta, rows, C, eps, gelu, stream);
-  else if (in_dtype == MVLT_BF16 && out_dtype == MVLT_F32) rc = launch_ln<bf16, float>(in, ld_in, out, ld_out, gamma, beta, rows, C, eps, gelu, stream);
+  if (in_dtype == MVLT_F32 && out_dtype == MVLT_F32) rc = launch_ln<float, float>(in, ld_in, out, ld_out, gamma, beta, rows, C, eps, gelu, out_bf16_copy, ld_copy, stream);
+  else if (in_dtype == MVLT_F32 && out_dtype == MVLT_BF16) rc = launch_ln<float, bf16>(in, ld_in, out, ld_out, gamma, beta, rows, C, eps, gelu, out_bf16_copy, ld_copy, stream);
+  else if (in_dtype == MVLT_BF16 && out_dtype == MVLT_BF16) rc = launch_ln<bf16, bf16>(in, ld_in, out, ld_out, gamma, beta, rows, C, eps, gelu, out_bf16_copy, ld_copy, stream);
+  else if (in_dtype == MVLT_BF16 && out_dtype == MVLT_F32) rc = launch_ln<bf16, float>(in, ld_in, out, ld_out, gamma, beta, rows, C, eps, gelu, out_bf16_copy, ld_copy, stream);
   else return MVLT_ERR_INVALID;
   if (rc != MVLT_OK) return rc;
   MVLT_LAUNCH_CHECK();
@@ -261,17 +270,17 @@ extern "C" int mvlt_patch_merge_ln(const float* x, void* out, int out_dtype, con
 
 extern "C" int mvlt_joint_embed(const void* feat, int feat_dtype, const int* img_index, const long long* ids,
                                 const unsigned char* text_mask, const unsigned char* image_mask, const float* word_emb,
-                                const float* typepos, void* out, int out_dtype, float* kmask, int B, int n_obj, int L,
-                                int D, int cls_id, int sep_id, cudaStream_t stream) {
-  if (!feat || !ids || !text_mask || !word_emb || !typepos || !out || !kmask || B <= 0 || n_obj <= 0 || L < 0) return MVLT_ERR_INVALID;
+                                const float* typepos, void* out, int out_dtype, void* out_bf16_copy, float* kmask, int B,
+                                int n_obj, int L, int D, int cls_id, int sep_id, cudaStream_t stream) {
+  if (!feat || !ids || !word_emb || !typepos || !out || !kmask || B <= 0 || n_obj <= 0 || L < 0) return MVLT_ERR_INVALID;
   if (D != 768) return MVLT_ERR_UNSUPPORTED;
   if (feat_dtype != out_dtype) return MVLT_ERR_INVALID;
   const long long rows = (long long)B * (n_obj + 2 + L);
   const unsigned grid = (unsigned)((rows + 7) / 8);
   if (out_dtype == MVLT_F32)
-    joint_embed_kernel<6, float, float><<<grid, 256, 0, stream>>>((const float*)feat, img_index, ids, text_mask, image_mask, word_emb, typepos, (float*)out, kmask, B, n_obj, L, D, cls_id, sep_id);
+    joint_embed_kernel<6, float, float><<<grid, 256, 0, stream>>>((const float*)feat, img_index, ids, text_mask, image_mask, word_emb, typepos, (float*)out, (bf16*)out_bf16_copy, kmask, B, n_obj, L, D, cls_id, sep_id);
   else if (out_dtype == MVLT_BF16)
-    joint_embed_kernel<6, bf16, bf16><<<grid, 256, 0, stream>>>((const bf16*)feat, img_index, ids, text_mask, image_mask, word_emb, typepos, (bf16*)out, kmask, B, n_obj, L, D, cls_id, sep_id);
+    joint_embed_kernel<6, bf16, bf16><<<grid, 256, 0, stream>>>((const bf16*)feat, img_index, ids, text_mask, image_mask, word_emb, typepos, (bf16*)out, (bf16*)out_bf16_copy, kmask, B, n_obj, L, D, cls_id, sep_id);
   else return MVLT_ERR_INVALID;
   MVLT_LAUNCH_CHECK();
   return MVLT_OK;

@@ -43,22 +43,34 @@ class MVLBertConfigforVQA(MVLBertConfig):
     _task_defaults = dict(MLM_task=True, ITM_task=True, result_num=224, lr=4e-5, attention_probs_dropout_prob=0.1,
                           hidden_dropout_prob=0.1)
 
+    def __init__(self, **kwargs):   # explicit: HF 5.x turns config classes into dataclasses and would synthesise one
+        super().__init__(**kwargs)
+
 
 class MVLBertPretrainConfig(MVLBertConfig):
     """reference config.py:41-50"""
     _task_defaults = dict(MLM_task=True, ITM_task=False, max_length=150, lr=4e-5, attention_probs_dropout_prob=0.1,
                           hidden_dropout_prob=0.1)
 
+    def __init__(self, **kwargs):   # explicit: HF 5.x turns config classes into dataclasses and would synthesise one
+        super().__init__(**kwargs)
+
 
 class MVLBertRetrieval(MVLBertConfig):
     """reference config.py:53-60"""
     _task_defaults = dict(ITM_task=True, lr=1e-6, max_length=80, attention_probs_dropout_prob=0.1)
+
+    def __init__(self, **kwargs):   # explicit: HF 5.x turns config classes into dataclasses and would synthesise one
+        super().__init__(**kwargs)
 
 
 class MVLBertConfigForImageCaption(MVLBertConfig):
     """reference config.py:64-72 (kept for config compatibility; the generation path itself is out of scope)."""
     _task_defaults = dict(lr=1e-5, max_length=80, is_decoder=True, attention_probs_dropout_prob=0.1,
                           hidden_dropout_prob=0.1)
+
+    def __init__(self, **kwargs):   # explicit: HF 5.x turns config classes into dataclasses and would synthesise one
+        super().__init__(**kwargs)
 
 
 def offline_config(task: str, conv: str = "swintransformer", max_length: int = 80, **overrides) -> MVLBertConfig:

@@ -182,6 +182,7 @@ class SwinTransformer(nn.Module):
         self.apply(self._init_weights)
         self._packed = None
         self._packed_key = None
+        self.taps = None   # tests set this to a dict to record block-boundary activations (clones)
 
     @staticmethod
     def _init_weights(m):  # vfe.py:659-666
@@ -234,12 +235,15 @@ class SwinTransformer(nn.Module):
         adt = act_dtype(self.precision)
         x = x.contiguous().float()
         X = ops.patch_embed_ln(x, pk["pe_w"], pk["pe_b"], pe.norm.weight, pe.norm.bias, pe.norm.eps)
+        taps = self.taps
+        if taps is not None:
+            taps["patch_embed"] = X.clone().view(B, -1, X.shape[-1])
         bi = 0
         for s, layer in enumerate(self.layers):
             H, W = layer.input_resolution
             C = layer.dim
             assert X.shape == (B * H * W, C), "input feature has wrong size"
-            for blk in layer.blocks:
+            for i, blk in enumerate(layer.blocks):
                 w = pk["blocks"][bi]
                 bi += 1
                 a = ops.layernorm(X, w["n1w"], w["n1b"], blk.norm1.eps, adt)
@@ -250,11 +254,15 @@ class SwinTransformer(nn.Module):
                 a = ops.layernorm(X, w["n2w"], w["n2b"], blk.norm2.eps, adt)
                 h = ops.linear(a, w["fc1_w"], w["fc1_b"], act=ops.ACT_GELU)
                 ops.linear(h, w["fc2_w"], w["fc2_b"], residual=X, out=X)
+                if taps is not None and i < 2:
+                    taps[f"s{s}b{i}"] = X.clone().view(B, H * W, C)
             if layer.downsample is not None:
                 m = pk["merge"][s]
                 assert H % 2 == 0 and W % 2 == 0, f"x size ({H}*{W}) are not even."
                 a = ops.patch_merge_ln(X, m["nw"], m["nb"], B, H, W, C, adt, layer.downsample.norm.eps)
                 X = ops.linear(a, m["red_w"], out_dtype=torch.float32)
+            if taps is not None:
+                taps[f"stage{s}"] = X.clone().view(B, -1, X.shape[-1])
         out = ops.layernorm(X, self.norm.weight, self.norm.bias, self.norm.eps, out_dtype or torch.float32, gelu=final_gelu)
         return out.view(B, -1, self.num_features)
 

@@ -71,16 +71,18 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out_dtype: torch.dtype,
-              gelu: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              gelu: bool = False, out: Optional[torch.Tensor] = None, bf16_copy: bool = False):
+    """LayerNorm rows.  bf16_copy=True additionally returns the rows rounded to bf16 (-> (out, copy))."""
     lib = _lib.ensure_init()
     rows, C, ld = _rows2d(x)
     if out is None:
         out = torch.empty((rows, C), device=x.device, dtype=out_dtype)
     _, _, ldo = _rows2d(out)
+    copy = torch.empty((rows, C), device=x.device, dtype=torch.bfloat16) if bf16_copy else None
     rc = lib.mvlt_layernorm_rows(x.data_ptr(), _code(x), ld, out.data_ptr(), _code(out), ldo, gamma.data_ptr(),
-                                 beta.data_ptr(), rows, C, float(eps), int(gelu), _stream())
+                                 beta.data_ptr(), rows, C, float(eps), int(gelu), _ptr(copy), C, _stream())
     _lib.check(rc, "mvlt_layernorm_rows")
-    return out
+    return (out, copy) if bf16_copy else out
 
 
 def patch_embed_ln(img: torch.Tensor, w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
@@ -121,17 +123,17 @@ def window_attention(qkv: torch.Tensor, relbias: torch.Tensor, B: int, H: int, W
     return out
 
 
-def joint_embed(feat: torch.Tensor, ids: torch.Tensor, text_mask: torch.Tensor, image_mask: Optional[torch.Tensor],
+def joint_embed(feat: torch.Tensor, ids: torch.Tensor, text_mask: Optional[torch.Tensor], image_mask: Optional[torch.Tensor],
                 word_emb: torch.Tensor, typepos: torch.Tensor, cls_id: int, sep_id: int,
-                img_index: Optional[torch.Tensor] = None):
-    """-> (hidden [B*S, D] in feat.dtype, kmask fp32 [B, S])"""
+                img_index: Optional[torch.Tensor] = None, bf16_copy: bool = False):
+    """-> (hidden [B*S, D] in feat.dtype, bf16 copy or None, kmask fp32 [B, S])"""
     lib = _lib.ensure_init()
     B, L = ids.shape
     n_obj, D = feat.shape[-2], feat.shape[-1]
     S = n_obj + 2 + L
     assert feat.is_contiguous() and ids.dtype == torch.int64 and ids.is_contiguous()
     assert typepos.shape[0] >= S and typepos.dtype == torch.float32 and word_emb.dtype == torch.float32
-    tm = text_mask.to(torch.uint8).contiguous()
+    tm = None if text_mask is None else text_mask.to(torch.uint8).contiguous()
     im = None if image_mask is None else image_mask.to(torch.uint8).contiguous()
     if img_index is not None:
         assert img_index.dtype == torch.int32 and img_index.numel() == B
@@ -139,11 +141,12 @@ def joint_embed(feat: torch.Tensor, ids: torch.Tensor, text_mask: torch.Tensor, 
         assert feat.shape[0] == B
     out = torch.empty((B * S, D), device=feat.device, dtype=feat.dtype)
     kmask = torch.empty((B, S), device=feat.device, dtype=torch.float32)
-    rc = lib.mvlt_joint_embed(feat.data_ptr(), _code(feat), _ptr(img_index), ids.data_ptr(), tm.data_ptr(), _ptr(im),
-                              word_emb.data_ptr(), typepos.data_ptr(), out.data_ptr(), _code(out), kmask.data_ptr(), B,
-                              n_obj, L, D, int(cls_id), int(sep_id), _stream())
+    copy = torch.empty((B * S, D), device=feat.device, dtype=torch.bfloat16) if bf16_copy else None
+    rc = lib.mvlt_joint_embed(feat.data_ptr(), _code(feat), _ptr(img_index), ids.data_ptr(), _ptr(tm), _ptr(im),
+                              word_emb.data_ptr(), typepos.data_ptr(), out.data_ptr(), _code(out), _ptr(copy),
+                              kmask.data_ptr(), B, n_obj, L, D, int(cls_id), int(sep_id), _stream())
     _lib.check(rc, "mvlt_joint_embed")
-    return out, kmask
+    return out, copy, kmask
 
 
 def joint_attention(qkv: torch.Tensor, kmask: torch.Tensor, B: int, S: int, heads: int, seq2seq: bool, obj_end: int,

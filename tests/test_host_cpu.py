@@ -1,0 +1,121 @@
+"""CPU suite, part 2: host logic, the C ABI surface, and the world_size-2 sharding path (gloo)."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def test_cabi_library_loads_and_exports_every_declared_symbol():
+    from medical_vision_langauge_transformer_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "mvlt_b200.h")).read()
+    declared = set(re.findall(r"^int (mvlt_\w+)\(", header, flags=re.M))
+    assert len(declared) >= 13
+    lib = _lib.load()                                    # dlopen only: no CUDA context, no compute
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/mvlt_b200.h but not exported"
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    assert lib.mvlt_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (mvlt_\w+)", out))
+    assert declared <= exported
+
+
+def test_ops_fail_loudly_without_a_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from medical_vision_langauge_transformer_b200 import _lib, ops
+    with pytest.raises((_lib.MvltNativeError, AssertionError)):
+        ops.softmax_rows(torch.zeros(2, 2))
+
+
+@pytest.mark.parametrize("task", ["vqa", "retrieval", "pretrain"])
+def test_state_dict_layout_matches_reference(task):
+    from medical_vision_langauge_transformer_b200.modules import config as C, model as M
+    ref = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))[task]
+    cls = {"vqa": M.MVLBertForVQA, "retrieval": M.MVLBertForRetrieval, "pretrain": M.MVLBertForPretraining}[task]
+    sd = cls(C.offline_config(task)).state_dict()
+    assert list(sd) == list(ref)                         # same keys, same order
+    assert all(list(sd[k].shape) == ref[k] for k in ref)
+
+
+def test_config_classes_mirror_reference_defaults():
+    from medical_vision_langauge_transformer_b200.modules import config as C
+    v, p, r = C.MVLBertConfigforVQA(), C.MVLBertPretrainConfig(), C.MVLBertRetrieval()
+    assert (v.type_vocab_size, v.result_num, v.hidden_dropout_prob, v.conv) == (3, 224, 0.1, "resnet101")
+    assert (p.MLM_task, p.ITM_task, p.max_length) == (True, False, 150)
+    assert (r.max_length, r.lr, r.hidden_dropout_prob, r.attention_probs_dropout_prob) == (80, 1e-6, 0.0, 0.1)
+    assert (v.hidden_size, v.num_hidden_layers, v.intermediate_size, v.layer_norm_eps) == (768, 12, 3072, 1e-12)
+
+
+def test_synth_is_deterministic_and_shaped():
+    from medical_vision_langauge_transformer_b200 import synth
+    a, b = synth.synth_token_ids(4, 80, 1), synth.synth_token_ids(4, 80, 1)
+    assert torch.equal(a, b) and a.dtype == torch.int64
+    for row in a:
+        n = int((row > 0).sum())
+        assert 10 <= n <= 80 and row[n - 1] == 104 and (row[n:] == 0).all() and (row[:n - 1] >= 1000).all()
+    m, l = synth.synth_mlm_labels(a, 1)
+    assert ((l != -100).sum(1) <= 10).all() and ((m == 103) == (l != -100)).all()
+    assert torch.equal(synth.synth_tensor("x.weight", (4, 8), 0), synth.synth_tensor("x.weight", (4, 8), 0))
+    assert not torch.equal(synth.synth_tensor("x.weight", (4, 8), 0), synth.synth_tensor("y.weight", (4, 8), 0))
+
+
+def test_shard_rows_partitions_exactly():
+    from medical_vision_langauge_transformer_b200.retrieval import shard_rows
+    for n in (0, 1, 7, 8, 2000, 2001):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_rows(n, r, world) for r in range(world)]
+            covered = [i for lo, hi in blocks for i in range(lo, hi)]
+            assert covered == list(range(n))
+            assert max(hi - lo for lo, hi in blocks) <= -(-n // world) if n else True
+
+
+def test_compute_ranks_matches_reference_semantics():
+    from medical_vision_langauge_transformer_b200 import retrieval
+    from oracle import mvlt_oracle as O
+    g = torch.load(os.path.join(GOLDEN, "rank6.pt"))
+    assert retrieval.compute_ranks(g["scores"], g["labels"]) == O.compute_ranks(g["scores"].numpy(), g["labels"].numpy())
+    rng = np.random.default_rng(0)
+    s = rng.random((9, 9)).astype(np.float32)
+    s[3, 4] = s[3, 5]                                    # a tie: numpy argsort order must decide, as in the reference
+    lab = np.eye(9, dtype=np.int64)
+    lab[2] = 0                                           # a row with no positive -> rank N (run_retrieval.py:231)
+    mine, ref = retrieval.compute_ranks(s, lab), O.compute_ranks(s, lab)
+    assert mine == ref and mine[0][2] == 9
+    ev = retrieval.evaluate(s, lab)
+    assert ev["i2t_retrieval"]["R@10"] == sum(r < 10 for r in ref[0]) / 9
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from medical_vision_langauge_transformer_b200.retrieval import shard_rows, all_gather_scores
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+N, NC = 7, 5
+full = torch.arange(N * NC, dtype=torch.float32).view(N, NC)
+lo, hi = shard_rows(N, dist.get_rank(), 2)
+out = all_gather_scores(full[lo:hi].clone(), N, 2)
+assert torch.equal(out, full), out
+dist.destroy_process_group()
+print("ok")
+"""
+
+
+def test_row_sharded_all_gather_world2_gloo(tmp_path):
+    """The N>1 path of the retrieval job on CPU: 2 processes, uneven shards (7 rows), one all-gather."""
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)

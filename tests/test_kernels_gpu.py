@@ -200,7 +200,7 @@ def test_joint_embed_and_attention(cuda, L, seq2seq):
           "MVLBert.token_type_embeddings.weight": rnd(3, D, seed=5)}
     pos = torch.arange(S, device="cuda")
     typepos = sd["MVLBert.token_type_embeddings.weight"][(pos <= 50).long()] + sd["MVLBert.position_embeddings.weight"][pos]
-    h, kmask = ops.joint_embed(feat, ids, ids > 0, None, sd["MVLBert.word_embeddings.weight"], typepos.contiguous(), 101, 102)
+    h, _, kmask = ops.joint_embed(feat, ids, ids > 0, None, sd["MVLBert.word_embeddings.weight"], typepos.contiguous(), 101, 102)
     ref_h = O.joint_embedding({k: v.cpu() for k, v in sd.items()}, ids.cpu(), feat.cpu())
     assert relerr(h.view(B, S, D).cpu(), ref_h) < 1e-6
     ref_mask = O.joint_attention_mask(ids.cpu(), 49, False)[:, 0, 0]

@@ -1,0 +1,107 @@
+"""CPU suite, part 1: the oracle restatement is pinned against outputs of the REAL reference (golden fixtures), and —
+when the reference tree is present (build container only) — against the reference executed live."""
+import os
+import random
+
+import pytest
+import torch
+
+from medical_vision_langauge_transformer_b200 import synth
+from oracle import mvlt_oracle as O
+from oracle.make_golden import probe_indices
+from oracle.ref_shims import reference_available
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _shapes(task):
+    import json
+    return {k: torch.Size(v) for k, v in json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))[task].items()}
+
+
+def _sd(task, seed, flavour):
+    return synth.synth_state_dict(_shapes(task), seed, flavour)
+
+
+def _check_taps(taps, golden_taps, tol=2e-5):
+    for name, g in golden_taps.items():
+        if name not in taps:
+            continue
+        t = taps[name].float().contiguous()
+        assert tuple(t.shape) == tuple(g["shape"]), name
+        v = t.flatten()[probe_indices(t.numel(), name)]
+        assert (v - g["values"]).abs().max().item() <= tol * max(g["absmax"], 1e-12), name
+
+
+@pytest.mark.parametrize("case", ["retrieval_stress", "retrieval_config1"])
+def test_oracle_retrieval_matches_reference_golden(case):
+    g = torch.load(os.path.join(GOLDEN, case + ".pt"))
+    sd = _sd("retrieval", g["weight_seed"], g["flavour"])
+    x, ids = synth.synth_images(g["B"], g["data_seed"], g["img_scale"]), synth.synth_token_ids(g["B"], g["L"], g["data_seed"])
+    taps = {}
+    with torch.no_grad():
+        prob = O.retrieval_forward(sd, x, ids, taps=taps)
+        logits = O.retrieval_forward(sd, x, ids, return_logits=True)
+    assert torch.allclose(prob, g["prob"], atol=1e-6) and torch.allclose(logits, g["logits"], atol=1e-5)
+    _check_taps(taps, g["taps"])
+
+
+def test_oracle_vqa_matches_reference_golden():
+    g = torch.load(os.path.join(GOLDEN, "vqa_stress.pt"))
+    sd = _sd("vqa", g["weight_seed"], g["flavour"])
+    x = synth.synth_images(g["B"], g["data_seed"], g["img_scale"])
+    ids = synth.synth_token_ids(g["B"], g["L"], g["data_seed"], min_len=g["min_len"])
+    taps = {}
+    with torch.no_grad():
+        prob, logits = O.vqa_forward(sd, x, ids, taps=taps)
+    assert torch.allclose(logits, g["logits"], atol=1e-5) and torch.allclose(prob, g["prob"], atol=1e-6)
+    assert torch.equal(prob.argmax(-1), g["prob"].argmax(-1))
+    _check_taps(taps, g["taps"])
+
+
+def test_oracle_pretrain_matches_reference_golden():
+    g = torch.load(os.path.join(GOLDEN, "pretrain_stress.pt"))
+    sd = _sd("pretrain", g["weight_seed"], g["flavour"])
+    x, ids = synth.synth_images(g["B"], g["data_seed"], g["img_scale"]), synth.synth_token_ids(g["B"], g["L"], g["data_seed"])
+    masked, labels = synth.synth_mlm_labels(ids, g["data_seed"])
+    for branch in ("seq2seq", "bidir"):
+        random.seed(g[branch]["py_seed"])
+        assert (random.random() < 0.5) == (branch == "seq2seq")
+        with torch.no_grad():
+            loss = O.pretrain_forward(sd, x, masked, labels, g["itm_labels"], seq2seq=branch == "seq2seq")
+        assert abs(loss.item() - g[branch]["loss"].item()) < 1e-5
+
+
+def test_oracle_rank_matrix_matches_reference_golden():
+    g = torch.load(os.path.join(GOLDEN, "rank6.pt"))
+    sd = _sd("retrieval", g["weight_seed"], "stress")
+    imgs, caps = synth.synth_images(g["N"], g["data_seed"], 1.0), synth.synth_token_ids(g["N"], g["L"], g["data_seed"])
+    with torch.no_grad():
+        scores = O.retrieval_score_matrix(sd, imgs[:2], caps)          # two rows keep the CPU suite short
+    assert torch.allclose(scores, g["scores"][:2], atol=1e-6)
+    i2t, t2i = O.compute_ranks(g["scores"].numpy(), g["labels"].numpy())
+    assert len(i2t) == len(t2i) == g["N"] and all(0 <= r <= g["N"] for r in i2t + t2i)
+
+
+def test_mask_and_index_restatements_match_reference_buffers():
+    """vfe.py:203-214 and :318-344 as restated in the oracle == the buffers the package modules register."""
+    from medical_vision_langauge_transformer_b200.modules.visual_feature_extractor import SwinTransformerBlock
+    for H in (56, 28, 14):
+        blk = SwinTransformerBlock(96, (H, H), 3, 7, 3)
+        assert torch.equal(blk.attn_mask, O.shift_attn_mask(H, H, 7, 3))
+        assert torch.equal(blk.attn.relative_position_index, O.relative_position_index(7))
+
+
+def test_flops_per_pair_matches_baseline_md():
+    assert abs(O.flops_per_pair(80) / 1e9 - 40.37) < 0.05
+    assert abs(O.flops_per_pair(23) / 1e9 - 30.25) < 0.05
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree only exists in the build container")
+def test_oracle_vs_live_reference():
+    from oracle.ref_shims import build_reference_model
+    m = build_reference_model("retrieval")
+    sd = synth.load_synth(m, seed=9, flavour="stress")
+    x, ids = synth.synth_images(2, 21, 1.0), synth.synth_token_ids(2, 80, 21)
+    with torch.no_grad():
+        assert torch.allclose(m(x, ids), O.retrieval_forward(sd, x, ids), atol=1e-6)
