@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — image-text pairs/sec, forward, Swin-S + BERT-base, 224x224, L=80 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--max-length L]
+
+A "step" is one forward of one batch of synthetic pairs through MVLBertForVQA (BASELINE.json configs[1]: Med-VQA
+forward + classifier head, batch 64 per GPU, bf16) — Swin trunk + joint BERT encoder + pooler + Linear(768,224) + softmax.
+Prints ONE JSON line (rank 0).  Keys: see the contract in DESIGN.md §Measurement.
+  value : whole-job pairs/s with inputs resident in HBM (CUDA-graph replay; K steps between CUDA events, max over ranks)
+  e2e   : same metric through runtime.GraphRunner with HOST pinned inputs; H2D of images+ids and D2H of prob/logits every
+          step inside the timed region
+  roofline     : the tcgen05 GEMM kernel (dominant: ~97% of FLOPs), live CUDA-event timing of every GEMM launch of a step
+  cpu_baseline : the CPU oracle port (same forward, torch fp32 on the host cores) on a bounded sample, rank 0, N=1 only
+--impl reference times that CPU port alone (the reference is pure Python/PyTorch and cannot travel to the GPU box; the
+oracle is its pinned restatement), all host threads, bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "image-text pairs/sec fwd (Swin-S+BERT, 224^2, L=80)"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="pairs per GPU per step")
+    ap.add_argument("--max-length", type=int, default=80)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"bf16_burst": p["bf16_tflops"], "bf16_sustained": p["bf16_tflops_sustained"], "hbm": p["hbm_gbs"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.lines, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_pairs_per_s(batch: int, L: int, min_seconds: float = 10.0, max_runs: int = 12):
+    """The reference forward (oracle port, torch fp32) on the host cores: VQA forward on `batch` pairs, repeated."""
+    import torch
+    from medical_vision_langauge_transformer_b200 import synth
+    from medical_vision_langauge_transformer_b200.modules import config as C, model as M
+    from oracle import mvlt_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = M.MVLBertForVQA(C.offline_config("vqa", max_length=L)).eval()
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    x, ids = synth.synth_images(batch, 1, 0.02), synth.synth_token_ids(batch, L, 1)
+    times = []
+    with torch.no_grad():
+        O.vqa_forward(sd, x[:1], ids[:1])                                   # warm-up (thread pool, allocator)
+        t_start = time.perf_counter()
+        while len(times) < 2 or (time.perf_counter() - t_start < min_seconds and len(times) < max_runs):
+            t0 = time.perf_counter()
+            O.vqa_forward(sd, x, ids)
+            times.append(time.perf_counter() - t0)
+    best = min(times)
+    return batch / best, threads, f"VQA forward, batch {batch}, L={L}, fp32, best of {len(times)} runs ({sum(times):.1f}s of CPU work)"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from medical_vision_langauge_transformer_b200 import synth
+    from medical_vision_langauge_transformer_b200.modules import config as C, model as M
+    from oracle import mvlt_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    b, L = args.cpu_sample_batch, args.max_length
+    torch.manual_seed(0)
+    model = M.MVLBertForVQA(C.offline_config("vqa", max_length=L)).eval()
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    x, ids = synth.synth_images(b, 1, 0.02), synth.synth_token_ids(b, L, 1)
+    steps, warm = min(args.steps, 20), min(args.warmup, 3)
+    with torch.no_grad():
+        for _ in range(max(warm, 1)):
+            O.vqa_forward(sd, x, ids)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.vqa_forward(sd, x, ids)
+        dt = time.perf_counter() - t0
+    v = b * steps / dt
+    sample = f"each step = VQA forward on a {b}-pair sample of the batch-{args.batch} workload, L={L}, fp32, {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": f"vqa_fwd_b{args.batch}_L{L}_swinS_bertbase", "sample_batch": b},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def gemm_roofline(model, x, ids, pk, steps=3):
+    """Live CUDA-event timing of every tcgen05 GEMM launch of a forward (eager, current stream): algorithmic FLOPs
+    (2*M*N*K, unpadded) / summed device time."""
+    import torch
+    from medical_vision_langauge_transformer_b200 import ops
+    records, orig = [], ops.linear
+
+    def timed_linear(a, w, *args, **kw):
+        if a.dtype != torch.bfloat16:
+            return orig(a, w, *args, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig(a, w, *args, **kw)
+        e1.record()
+        M = a.numel() // a.shape[-1] if a.dim() != 2 else a.shape[0]
+        records.append((e0, e1, 2.0 * M * w.shape[0] * w.shape[1], (M, w.shape[0], w.shape[1])))
+        return out
+
+    per_step = []
+    try:
+        ops.linear = timed_linear
+        for mod in list(sys.modules.values()):
+            if getattr(mod, "__name__", "").startswith("medical_vision_langauge_transformer_b200.modules") and hasattr(mod, "ops"):
+                mod.ops.linear = timed_linear
+        with torch.no_grad():
+            for _ in range(steps + 1):
+                records.clear()
+                model(x, ids, None)
+                torch.cuda.synchronize()
+                per_step.append([(e0.elapsed_time(e1) * 1e-3, fl, shp) for e0, e1, fl, shp in records])
+    finally:
+        ops.linear = orig
+    last = per_step[1:]                                                     # drop the first (cold) pass
+    t = sum(sum(r[0] for r in st) for st in last) / len(last)
+    fl = sum(r[1] for r in last[0])
+    by_shape = {}
+    for st in last:
+        for dt, f, shp in st:
+            d = by_shape.setdefault(shp, [0.0, 0.0, 0])
+            d[0] += dt / len(last); d[1] += f / len(last); d[2] += 1.0 / len(last)
+    achieved = fl / t / 1e12
+    return {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / pk["bf16_sustained"], "traffic": None,
+            "kernel": "gemm_tc_kernel (tcgen05 bf16, all nn.Linear sites)", "launches_per_step": len(last[0]),
+            "gemm_ms_per_step": t * 1e3, "gemm_flop_per_step": fl, "peak_source": pk["source"] + ", sustained figure",
+            "frac_of_burst_peak": achieved / pk["bf16_burst"]}, by_shape
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from medical_vision_langauge_transformer_b200 import runtime, synth
+    from medical_vision_langauge_transformer_b200.modules import config as C, model as M
+    from oracle import mvlt_oracle as O          # FLOP accounting only (flops_per_pair); never on the timed path
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (sm_100a); there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, L = args.batch, args.max_length
+    pk = peaks()
+
+    torch.manual_seed(0)                                                     # random init of the reference architecture
+    model = M.MVLBertForVQA(C.offline_config("vqa", max_length=L)).eval().to(dev).set_precision(args.precision)
+    n_rot = 4                                                                # rotate distinct batches: inputs never L2-resident
+    imgs = [synth.synth_images(B, 100 + rank * 16 + i, 0.02) for i in range(n_rot)]
+    idss = [synth.synth_token_ids(B, L, 100 + rank * 16 + i) for i in range(n_rot)]
+    d_imgs, d_ids = [t.to(dev) for t in imgs], [t.to(dev) for t in idss]
+    h_imgs, h_ids = [t.pin_memory() for t in imgs], [t.pin_memory() for t in idss]
+
+    runner = runtime.GraphRunner(lambda im, tx: model(im, tx, None), (d_imgs[0], d_ids[0]), slots=2)
+    launches = runner.launches_per_replay
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput: K graph replays between two events on the compute stream
+    def resident(k):
+        for i in range(k):
+            slot = i % 2
+            with torch.cuda.stream(runner.compute):
+                runner.static_in[slot][0].copy_(d_imgs[i % n_rot], non_blocking=True)   # D2D refresh (38.5 MB) keeps inputs distinct
+                runner.static_in[slot][1].copy_(d_ids[i % n_rot], non_blocking=True)
+            runner.replay(slot)
+
+    resident(args.warmup)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(runner.compute)
+    resident(args.steps)
+    e1.record(runner.compute)
+    barrier()
+    t_res = e0.elapsed_time(e1) * 1e-3
+
+    # ---- end-to-end: pinned host inputs -> H2D -> graph -> D2H of (prob, logits), every step, pipelined over 2 slots
+    def e2e(k):
+        pending = []
+        for i in range(k):
+            if len(pending) == runner.slots:
+                runner.result(pending.pop(0))
+            pending.append(runner.submit((h_imgs[i % n_rot], h_ids[i % n_rot])))
+        for s in pending:
+            runner.result(s)
+
+    e2e(args.warmup)
+    barrier()
+    w0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(runner.copy)
+    e2e(args.steps)
+    g1.record(runner.compute)
+    barrier()
+    t_e2e_wall = time.perf_counter() - w0
+    t_e2e = max(g0.elapsed_time(g1) * 1e-3, 0.0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([t_res, t_e2e, t_e2e_wall], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_res, t_e2e, t_e2e_wall = t.tolist()
+
+    roof, by_shape, cpu = None, None, None
+    if rank == 0 and not args.no_roofline and args.precision == "bf16":
+        roof, by_shape = gemm_roofline(model, d_imgs[0], d_ids[0], pk)
+        prof = os.path.join(ROOT, "profiles", "gemm_tc_traffic.json")
+        if os.path.exists(prof):
+            roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, sample = cpu_port_pairs_per_s(args.cpu_sample_batch, L)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        pairs = world * B * args.steps
+        value = pairs / t_res
+        flop_pair = O.flops_per_pair(L) - 2 * 768 * 768 + 2 * 768 * 224           # pooler + Linear(768,224) instead of pooler + transform
+        out_bytes = sum(o.numel() * o.element_size() for o in runner.static_out[0])
+        res = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"vqa_fwd_b{B}_L{L}_swinS_bertbase (BASELINE.json configs[1] at the metric's L=80)",
+                       "batch_per_gpu": B, "max_length": L, "joint_seq": 51 + L, "result_num": 224, "weights": "random init, seed 0",
+                       "parallelism": f"dp{world} (batch-sharded, no collective in the forward)",
+                       "l2": "4 distinct input batches rotated (154 MB) + 323 MB bf16 weights + >1 GB activations per step: working set >> 126 MB L2",
+                       "launch": "CUDA graph replay"},
+            "e2e": {"value": pairs / t_e2e, "unit": UNIT, "h2d_bytes_per_step": B * (3 * 224 * 224 * 4 + L * 8),
+                    "d2h_bytes_per_step": out_bytes, "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "wall_pairs_per_s": pairs / t_e2e_wall, "api": "runtime.GraphRunner(model)(pinned images, pinned ids) -> (prob, logits) on host"},
+            "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+            "tensor_frac_whole_step": {"achieved_tflops": value * flop_pair / world / 1e12, "of_sustained_peak": value * flop_pair / world / 1e12 / pk["bf16_sustained"],
+                                       "gflop_per_pair": flop_pair / 1e9},
+            "clocks": clocks,
+        }
+        if roof:
+            res["roofline"] = roof
+            res["gemm_by_shape"] = {f"{m}x{n}x{k}": {"ms_per_step": round(v[0] * 1e3, 4), "tflops": round(v[1] / v[0] / 1e12, 1), "launches": round(v[2])}
+                                    for (m, n, k), v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])}
+        if cpu:
+            res["cpu_baseline"] = cpu
+        print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -11,11 +11,13 @@
 //   warp 1    : MMA issuer     — one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N, K=16),
 //                                accumulating into one of two TMEM accumulator stages (2 x 256 columns)
 //   warp 2    : TMEM allocator
-//   warps 4-11: epilogue       — tcgen05.ld 32x32b.x32 -> registers -> +bias -> GELU/tanh -> +residual -> store;
-//                                runs on accumulator stage i while the MMA warp fills stage i^1
+//   warps 4-11: epilogue       — tcgen05.ld 32x32b.x32 -> registers -> +bias -> GELU/tanh -> smem transpose ->
+//                                +residual -> coalesced 128 B row stores; runs on accumulator stage i while the MMA
+//                                warp fills stage i^1
 // BLOCK_N is a runtime value (multiple of 32, <= 256) carried in the instruction descriptor and the TMA box, so one
 // kernel serves N = 96 ... 3072.  M/N/K edges are handled by TMA zero fill on loads and guards on stores.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
@@ -32,7 +34,9 @@ constexpr int GEMM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
-constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * 32 * 32 * 4;  // one swizzled 32x32 fp32 tile per epilogue warp
+constexpr int GEMM_SMEM_BYTES =
+    STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGING_BYTES;
 
 struct GemmParams {
   void* C;
@@ -46,6 +50,7 @@ struct GemmParams {
   int out_dtype;  // MVLT_F32 / MVLT_BF16
   int res_dtype;  // -1 none, MVLT_F32, MVLT_BF16
   int tiles_m, tiles_n;
+  int debug;  // MVLT_GEMM_DEBUG bits (profiling experiments only): 1 = no epilogue global traffic, 2 = no MMA, 4 = no TMA
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -108,6 +113,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = 0; kb < num_kb; ++kb, ++kc) {
           const uint32_t s = kc % STAGES, ph = (kc / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
+          if (p.debug & 4) { mbar_arrive(&full_bar[s]); continue; }
           mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
           tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BK, m0);
           tma_load_2d(smem_b + s * B_STAGE_BYTES, &tmap_b, &full_bar[s], kb * BK, n0);
@@ -132,7 +138,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint64_t db = umma_desc_k_sw128(base + STAGES * A_STAGE_BYTES + s * B_STAGE_BYTES);
           const int ksteps = min(BK, p.K - kb * BK) / 16;  // K % 16 == 0 is checked on the host
 #pragma unroll 1
-          for (int k = 0; k < ksteps; ++k) {
+          for (int k = 0; k < ksteps && !(p.debug & 2); ++k) {
             // advance 16 elements = 32 B inside the 128 B swizzle span: +2 in the (addr >> 4) field
             umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
@@ -143,19 +149,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp >= EPI_WARP0) {
     // ------------------------------- epilogue -----------------------------------
+    // TMEM gives each thread one ROW of the 32x32 chunk; writing rows straight to global would touch 32 different
+    // 128 B lines per instruction.  So: bias + activation in the row layout, transpose through a per-warp 4 KB
+    // XOR-swizzled smem tile (conflict-free both ways), then residual add + convert + store in the COALESCED layout
+    // (8 lanes cover one row's 128 B, 4 rows per instruction).
     const int ew = warp - EPI_WARP0;
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the only ones this warp may touch
     const int half = ew >> 2;      // column half of the tile
     const int chunks = p.block_n / 32;
     const int c_begin = half * ((chunks + 1) / 2);
     const int c_end = half ? chunks : (chunks + 1) / 2;
-    const bool vec_ok = (p.ldc % 8 == 0) && (p.res_dtype < 0 || p.ldres % 8 == 0);  // 16 B aligned row starts
+    const bool vec_ok = (p.ldc % 4 == 0) && (p.res_dtype < 0 || p.ldres % 4 == 0);
+    float* stg = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256) + ew * 1024;
+    const int crow = lane >> 3, cch = lane & 7;  // coalesced layout: this lane's row-in-group and 16 B column chunk
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, acc_ph = (it >> 1) & 1;
-      const int m0 = (tile / p.tiles_n) * BM;
+      const int m0 = (tile / p.tiles_n) * BM + quarter * 32;
       const int n0 = (tile % p.tiles_n) * p.block_n;
-      const int m = m0 + quarter * 32 + lane;
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
       for (int c = c_begin; c < c_end; ++c) {
@@ -163,73 +174,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN_MAX + c * 32, r);
         tmem_ld_wait();
-        if (m < p.M && nb < p.N) {
-          float v[32];
+        if (nb >= p.N) continue;  // warp-uniform
+        const bool full_n = nb + 32 <= p.N;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (vec_ok && nb + 32 <= p.N) {
-            if (p.bias) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
-            }
-            if (p.act) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-            }
-            if (p.res_dtype == MVLT_F32) {
-              const float* rp = reinterpret_cast<const float*>(p.res) + (long long)m * p.ldres + nb;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 t = load4(rp + j);
-                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-              }
-            } else if (p.res_dtype == MVLT_BF16) {
-              const bf16* rp = reinterpret_cast<const bf16*>(p.res) + (long long)m * p.ldres + nb;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 u = *reinterpret_cast<const uint4*>(rp + j);
-                float2 t;
-                t = unpack_bf16x2(u.x); v[j] += t.x; v[j + 1] += t.y;
-                t = unpack_bf16x2(u.y); v[j + 2] += t.x; v[j + 3] += t.y;
-                t = unpack_bf16x2(u.z); v[j + 4] += t.x; v[j + 5] += t.y;
-                t = unpack_bf16x2(u.w); v[j + 6] += t.x; v[j + 7] += t.y;
-              }
-            }
-            if (p.out_dtype == MVLT_F32) {
-              float* cp = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + nb;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) store4(cp + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        for (int j = 0; j < 32; j += 4) {
+          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                 __uint_as_float(r[j + 3]));
+          if (p.bias) {
+            if (full_n) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
             } else {
-              bf16* cp = reinterpret_cast<bf16*>(p.C) + (long long)m * p.ldc + nb;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 u;
-                u.x = pack_bf16x2(v[j], v[j + 1]);
-                u.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                u.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                u.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(cp + j) = u;
-              }
+              if (nb + j < p.N) v.x += p.bias[nb + j];
+              if (nb + j + 1 < p.N) v.y += p.bias[nb + j + 1];
+              if (nb + j + 2 < p.N) v.z += p.bias[nb + j + 2];
+              if (nb + j + 3 < p.N) v.w += p.bias[nb + j + 3];
             }
+          }
+          if (p.act) {
+            v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
+            v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+          }
+          *reinterpret_cast<float4*>(stg + lane * 32 + ((((j >> 2) ^ (lane & 7))) << 2)) = v;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int row = g * 4 + crow;
+          const int m = m0 + row, n = nb + cch * 4;
+          float4 v = *reinterpret_cast<const float4*>(stg + row * 32 + ((cch ^ (row & 7)) << 2));
+          if (m >= p.M || n >= p.N || (p.debug & 1)) continue;
+          if (vec_ok && n + 4 <= p.N) {
+            if (p.res_dtype == MVLT_F32) {
+              const float4 t = load4(reinterpret_cast<const float*>(p.res) + (long long)m * p.ldres + n);
+              v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            } else if (p.res_dtype == MVLT_BF16) {
+              const float4 t = load4(reinterpret_cast<const bf16*>(p.res) + (long long)m * p.ldres + n);
+              v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            }
+            if (p.out_dtype == MVLT_F32) store4(reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + n, v);
+            else store4(reinterpret_cast<bf16*>(p.C) + (long long)m * p.ldc + n, v);
           } else {
-            // ragged edge: scalar, fully guarded
-#pragma unroll 1
-            for (int j = 0; j < 32; ++j) {
-              const int n = nb + j;
-              if (n >= p.N) break;
-              float x = v[j];
-              if (p.bias) x += p.bias[n];
-              x = apply_act(x, p.act);
-              if (p.res_dtype == MVLT_F32) x += reinterpret_cast<const float*>(p.res)[(long long)m * p.ldres + n];
-              else if (p.res_dtype == MVLT_BF16) x += to_f32(reinterpret_cast<const bf16*>(p.res)[(long long)m * p.ldres + n]);
-              if (p.out_dtype == MVLT_F32) reinterpret_cast<float*>(p.C)[(long long)m * p.ldc + n] = x;
-              else reinterpret_cast<bf16*>(p.C)[(long long)m * p.ldc + n] = __float2bfloat16_rn(x);
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (n + q >= p.N) break;
+              float x = e[q];
+              const long long ro = (long long)m * p.ldres + n + q, co = (long long)m * p.ldc + n + q;
+              if (p.res_dtype == MVLT_F32) x += reinterpret_cast<const float*>(p.res)[ro];
+              else if (p.res_dtype == MVLT_BF16) x += to_f32(reinterpret_cast<const bf16*>(p.res)[ro]);
+              if (p.out_dtype == MVLT_F32) reinterpret_cast<float*>(p.C)[co] = x;
+              else reinterpret_cast<bf16*>(p.C)[co] = __float2bfloat16_rn(x);
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -327,6 +326,11 @@ extern "C" int mvlt_gemm_bf16_tc(const void* A, long long lda, const void* W, lo
   p.M = M; p.N = N; p.K = K; p.block_n = block_n; p.act = act; p.out_dtype = out_dtype; p.res_dtype = res_dtype;
   p.tiles_m = (M + BM - 1) / BM;
   p.tiles_n = (N + block_n - 1) / block_n;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("MVLT_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   gemm_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta, tb, p);
