@@ -26,6 +26,25 @@ typedef __nv_bfloat16 bf16;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// erf-GELU for the tensor-core epilogues: 9 FP ops + ONE MUFU per element instead of erff's ~36 instructions.
+// erfc(|x|/sqrt2) = 2^-q(|x|), q = a*(c1 + a*(c2 + a*(c3 + a*(c4 + a*c5)))): -log2(erfc(t)) fitted on t in [0, 5.5] by
+// least squares on the erf error, with the 1/sqrt2 argument scale folded into the coefficients (q grows ~a^2 beyond
+// the fit range, so the tail saturates correctly).  Max |erf error| 7.9e-7, max |GELU error| 1.6e-6 over [-12, 12]
+// in fp32 arithmetic (fit + check: DESIGN.md §GELU).  The fp32 parity kernels keep erff.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float a = fabsf(x);
+  float q = fmaf(a, 0.0005292023415677249f, -0.007443261332809925f);
+  q = fmaf(q, a, 0.05264018476009369f);
+  q = fmaf(q, a, 0.45920330286026f);
+  q = fmaf(q, a, 1.1511013507843018f);
+  q = -q * a;
+  float erfc_a;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(erfc_a) : "f"(q));
+  const float e = copysignf(1.0f - erfc_a, x);
+  const float h = 0.5f * x;
+  return fmaf(h, e, h);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -99,6 +118,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
+}
+
+// One lane of a converged warp (the compiler keeps the guarded operands in uniform registers).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- TMA ---------------------------------------------------------------------------------------
