@@ -45,6 +45,43 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(h, e, h);
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 — two fp32 lanes per issued instruction) -------------
+__device__ __forceinline__ uint64_t f2_as_u64(float2 v) { return *reinterpret_cast<uint64_t*>(&v); }
+__device__ __forceinline__ float2 u64_as_f2(uint64_t v) { return *reinterpret_cast<float2*>(&v); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
+  return u64_as_f2(d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
+  return u64_as_f2(d);
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)), "l"(f2_as_u64(c)));
+  return u64_as_f2(d);
+}
+
+// gelu_erf_fast on a pair, arranged for the packed pipes.  With a = |x|, s = x*x and the same fitted q(a) = c1 a + c2 a^2 +
+// c3 a^3 + c4 a^4 + c5 a^5 split into even/odd powers:  q = a*(c1 + s*(c3 + s*c5)) + s*(c2 + s*c4), and
+//   GELU(x) = x*Phi(x) = relu(x) - a * 2^(-q - 1)            (Phi(-a) = erfc(a/sqrt2)/2 = 2^(-q-1))
+// -> 5 packed FMA/MUL + per lane {FFMA, MUFU.EX2, FMNMX, FFMA}: 6.5 issued instructions per element instead of 11.
+__device__ __forceinline__ float2 gelu_erf_fast2(float2 x) {
+  const float c1 = 1.1511013507843018f, c2 = 0.45920330286026f, c3 = 0.05264018476009369f, c4 = -0.007443261332809925f,
+              c5 = 0.0005292023415677249f;
+  const float2 s = mul2(x, x);
+  float2 A = fma2(s, make_float2(c5, c5), make_float2(c3, c3));
+  A = fma2(A, s, make_float2(c1, c1));
+  const float2 Bq = fma2(s, make_float2(c4, c4), make_float2(c2, c2));
+  const float2 u = fma2(s, Bq, make_float2(1.0f, 1.0f));
+  float t0, t1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(fmaf(-fabsf(x.x), A.x, -u.x)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(fmaf(-fabsf(x.y), A.y, -u.y)));
+  return make_float2(fmaf(-fabsf(x.x), t0, fmaxf(x.x, 0.0f)), fmaf(-fabsf(x.y), t1, fmaxf(x.y, 0.0f)));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -139,6 +176,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 2-D tiled store smem -> global (bulk async-group completion); out-of-bounds rows/columns are clipped by the TMA unit
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's bulk groups still READING their shared-memory source
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- tcgen05 / TMEM ----------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {

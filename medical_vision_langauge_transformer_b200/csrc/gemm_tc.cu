@@ -5,107 +5,93 @@
 // replaces: vfe.py:231 (qkv), :252 (proj), :136-139 (fc1/fc2), :443 (merge reduction);
 //           HF modeling_bert.py:179-181 (Q,K,V as one [2304,768] weight), :295, :338, :352, :476, :502 (MLM decoder).
 //
-// One persistent, warp-specialised kernel, templated on the CTA-group size CG:
-//   CG = 2 (default): a cluster of two CTAs (one SM pair) owns a 256 x BLOCK_N output tile.  Each CTA TMA-loads its
-//           own 128 rows of A and HALF of the W tile per 64-wide k-block; one thread of the leader CTA issues
-//           tcgen05.mma.cta_group::2 (M=256) which reads both CTAs' smem and writes both CTAs' TMEM.  Per SM this
-//           needs 32 KB of operands per 512 tensor cycles instead of 48 KB per 512 -> 6-stage ring, ~3x less
-//           L2->SM traffic per FLOP than the single-CTA tile.
-//   CG = 1: single-CTA 128 x BLOCK_N tiles (kept for A/B measurements: MVLT_GEMM_CTAS=1).
+// One persistent, warp-specialised kernel.  A cluster of two CTAs (one SM pair) owns a 256 x BLOCK_N output tile:
+// each CTA TMA-loads its own 128 rows of A and HALF of the W tile per 64-wide k-block, and one thread of the leader
+// CTA issues tcgen05.mma.cta_group::2 (M=256), which reads both CTAs' smem and writes both CTAs' TMEM.
 // Roles per CTA (384 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warp 2 TMEM allocator,
 // warps 4-11 epilogue.  Two TMEM accumulator stages (2 x 256 columns): the epilogue of tile i overlaps the MMAs of
-// tile i+1.  Epilogue: tcgen05.ld 32x32b.x32 -> +bias (smem-staged) -> GELU/tanh -> XOR-swizzled smem transpose ->
-// +residual -> 128 B-per-row coalesced stores.  BLOCK_N is a runtime value (multiple of 32, <= 256) carried by the
-// instruction descriptor and the TMA box.  M/N/K edges: TMA zero fill on loads, guards on stores.
+// tile i+1.
+//
+// Epilogue (the part that bounds every K <= 768 call site): the kernel is compiled per
+// (activation, output dtype, residual) so the inner loop carries no runtime switches.  Each epilogue warp owns
+// 32 accumulator rows (its TMEM lane quarter) and walks 32-column chunks:
+//   tcgen05.ld 32x32b.x32 -> + bias (packed fp32x2 adds) -> erf-GELU (packed FFMA2 polynomial + one MUFU) ->
+//   [+ residual, which a TMA load has already parked in this warp's staging buffer, in place] ->
+//   st.shared in the TMA swizzle pattern -> one cp.async.bulk.tensor store per chunk.
+// The residual chunk for step k+1 is prefetched while step k computes (3 staging buffers per warp), M/N edges are
+// clipped by the TMA unit, and no epilogue thread executes a global load/store or a bounds test per element.
+// BLOCK_N is a runtime value (multiple of 32, <= 256) carried by the instruction descriptor and the TMA boxes.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <math.h>
 #include <stdlib.h>
 
 #include "common.cuh"
 
 namespace mvlt {
 
+constexpr int CG = 2;    // CTAs per tile (cta_group::2)
 constexpr int BM = 128;  // rows per CTA
 constexpr int BK = 64;   // 64 bf16 = 128 B = one swizzle span
 constexpr int BN_MAX = 256;
-constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int A_STAGE_BYTES = BM * BK * 2;                // 16 KB
+constexpr int B_STAGE_BYTES = (BN_MAX / CG) * BK * 2;     // 16 KB: W rows held per CTA per stage
 constexpr int GEMM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_EPI_WARPS = 8;
+constexpr int EPI_PARTS = NUM_EPI_WARPS / 4;              // warps per TMEM lane quarter
 constexpr int TMEM_COLS = 512;
-constexpr int RING_BYTES = 192 * 1024;
-constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * 32 * 32 * 4;  // one swizzled 32x32 fp32 tile per epilogue warp
-constexpr int AUX_BYTES = 256 /*barriers*/ + BN_MAX * 4 /*bias*/;
-constexpr int GEMM_SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + AUX_BYTES + EPI_STAGING_BYTES;
+constexpr int AUX_BYTES = 512;
+constexpr int SMEM_LIMIT = 227 * 1024;
 
-template <int CG> struct Cfg {
-  static constexpr int B_STAGE_BYTES = (BN_MAX / CG) * BK * 2;  // W rows held per CTA per stage
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = RING_BYTES / STAGE_BYTES;  // 4 (CG=1) or 6 (CG=2)
+// Shared-memory plan of one kernel variant.  The operand ring wants depth (bytes in flight per SM = L2 latency x the
+// 64 B/clk the MMAs consume), the epilogue wants staging buffers; bf16 chunks are 2 KB (32 rows x 64 B), fp32 chunks
+// 4 KB (32 x 128 B), and only the residual variant needs a third buffer (prefetch of chunk k+1 while k-1 still drains).
+template <bool OUT_BF16, bool RES> struct Plan {
+  static constexpr int NBUF = RES ? 3 : 2;
+  static constexpr int BUF_BYTES = OUT_BF16 ? 2048 : 4096;
+  static constexpr int EPI_BYTES = NUM_EPI_WARPS * NBUF * BUF_BYTES;
+  static constexpr int STAGES = (SMEM_LIMIT - 1024 - AUX_BYTES - EPI_BYTES) / (A_STAGE_BYTES + B_STAGE_BYTES) > 6
+                                    ? 6 : (SMEM_LIMIT - 1024 - AUX_BYTES - EPI_BYTES) / (A_STAGE_BYTES + B_STAGE_BYTES);
+  static constexpr int RING_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + NUM_EPI_WARPS * NBUF;
+  static constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + AUX_BYTES + 1024 /*align slack*/;
+  static_assert(NUM_BARS * 8 + 8 <= AUX_BYTES, "barrier block too small");
+  static_assert(SMEM_BYTES <= SMEM_LIMIT && STAGES >= 4, "shared memory budget");
 };
 
 struct GemmParams {
-  void* C;
-  long long ldc;
   const float* bias;
-  const void* res;
-  long long ldres;
   int M, N, K;
   int block_n;
-  int act;        // 0 none, 1 erf-GELU, 2 tanh
-  int out_dtype;  // MVLT_F32 / MVLT_BF16
-  int res_dtype;  // -1 none, MVLT_F32, MVLT_BF16
   int tiles_m, tiles_n;
-  int debug;      // MVLT_GEMM_DEBUG bits (profiling experiments only): 1 no epilogue global traffic, 2 no MMA, 4 no TMA
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == 1) return gelu_erf_fast(v);
-  if (act == 2) return tanhf(v);
-  return v;
+// ---- cta_group::2 PTX ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst)), "r"(ncols) : "memory");
 }
-
-// ---- cta_group-templated PTX -----------------------------------------------------------------------------------
-template <int CG> __device__ __forceinline__ void tmem_alloc_cg(uint32_t* dst, uint32_t ncols) {
-  if (CG == 1) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst)), "r"(ncols) : "memory");
-  else asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst)), "r"(ncols) : "memory");
+__device__ __forceinline__ void tmem_relinquish_cg2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
-template <int CG> __device__ __forceinline__ void tmem_relinquish_cg() {
-  if (CG == 1) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  else asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-template <int CG> __device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr, uint32_t ncols) {
-  if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
-template <int CG>
-__device__ __forceinline__ void umma_bf16_cg(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  if (CG == 1)
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-  else
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+// mbarrier arrive (on the same barrier of BOTH CTAs of the pair) once all MMAs issued so far by this thread retire
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
-// mbarrier arrive once all MMAs issued so far by this thread retire; CG=2: on the same barrier of BOTH CTAs of the pair
-template <int CG> __device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
-  if (CG == 1)
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-  else
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-// TMA tile load into THIS CTA's smem; CG=2: completion bytes are counted on the LEADER CTA's mbarrier (peer bit cleared)
-template <int CG>
-__device__ __forceinline__ void tma_load_cg(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
-  if (CG == 1) {
-    tma_load_2d(smem_dst, tmap, bar, c0, c1);
-  } else {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
-        : "memory");
-  }
+// TMA tile load into THIS CTA's smem; completion bytes are counted on the LEADER CTA's mbarrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_cg2(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -121,30 +107,33 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int CG>
+// ACT: 0 none, 1 erf-GELU, 2 tanh.  OUT_BF16: C is bf16 (else fp32).  RES: C += residual (fp32, via tmap_r; fp32 C only).
+template <int ACT, bool OUT_BF16, bool RES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p) {
-  using C = Cfg<CG>;
-  constexpr int STAGES = C::STAGES;
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, GemmParams p) {
+  static_assert(!(RES && OUT_BF16), "residual epilogue is fp32-in/fp32-out");
+  using P = Plan<OUT_BF16, RES>;
+  constexpr int STAGES = P::STAGES, EPI_NBUF = P::NBUF, EPI_BUF_BYTES = P::BUF_BYTES, RING_BYTES = P::RING_BYTES;
+  constexpr int EPI_BYTES = P::EPI_BYTES, NUM_BARS = P::NUM_BARS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING_BYTES);
+  uint8_t* smem_epi = smem + RING_BYTES;                 // 1024 B aligned (RING_BYTES is a multiple of 1024)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING_BYTES + EPI_BYTES);
   uint64_t* full_bar = bars;                     // [STAGES]  TMA -> MMA        (lives in the leader CTA)
   uint64_t* empty_bar = bars + STAGES;           // [STAGES]  MMA -> TMA        (one copy per CTA)
   uint64_t* tmem_full = bars + 2 * STAGES;       // [2]       MMA -> epilogue   (one copy per CTA)
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]       epilogue -> MMA   (leader CTA)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* bias_s = reinterpret_cast<float*>(smem + RING_BYTES + 256);
-  float* staging = reinterpret_cast<float*>(smem + RING_BYTES + AUX_BYTES);
+  uint64_t* res_full = bars + 2 * STAGES + 4;    // [NUM_EPI_WARPS][EPI_NBUF]  residual TMA -> epilogue warp
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
+  const uint32_t rank = cluster_ctarank();
   const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int num_kb = (p.K + BK - 1) / BK;
@@ -153,6 +142,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_c);
+    if (RES) tma_prefetch_desc(&tmap_r);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -163,14 +154,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], CG * NUM_EPI_WARPS);
     }
+    for (int s = 0; s < NUM_EPI_WARPS * EPI_NBUF; ++s) mbar_init(&res_full[s], 1);
     mbar_fence_init();
   }
   if (warp == 2) {
-    tmem_alloc_cg<CG>(tmem_ptr, TMEM_COLS);
-    tmem_relinquish_cg<CG>();
+    tmem_alloc_cg2(tmem_ptr, TMEM_COLS);
+    tmem_relinquish_cg2();
   }
   tc_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -189,13 +181,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t s = kc % STAGES, ph = (kc / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (elect_one()) {
-          if (p.debug & 4) {
-            if (rank == 0) mbar_arrive(&full_bar[s]);
-          } else {
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-            tma_load_cg<CG>(smem_a + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BK, m0);
-            tma_load_cg<CG>(smem_b + s * C::B_STAGE_BYTES, &tmap_b, &full_bar[s], kb * BK, n0);
-          }
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+          tma_load_cg2(smem_a + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BK, m0);
+          tma_load_cg2(smem_b + s * B_STAGE_BYTES, &tmap_b, &full_bar[s], kb * BK, n0);
         }
         __syncwarp();
       }
@@ -219,18 +207,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t lo_a = lo_a0 + s * (A_STAGE_BYTES >> 4);
-          const uint32_t lo_b = lo_b0 + s * (C::B_STAGE_BYTES >> 4);
+          const uint32_t lo_b = lo_b0 + s * (B_STAGE_BYTES >> 4);
           const int ksteps = min(BK, p.K - kb * BK) / 16;  // K % 16 == 0 is checked on the host
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // advance 16 elements = 32 B inside the 128 B swizzle span: +2 in the (addr >> 4) field
-              if (k < ksteps && !(p.debug & 2))
-                umma_bf16_cg<CG>(tmem_d, ((uint64_t)DESC_HI << 32) | (lo_a + 2 * k), ((uint64_t)DESC_HI << 32) | (lo_b + 2 * k),
-                                 idesc, (kb | k) != 0);
+              if (k < ksteps)
+                umma_bf16_cg2(tmem_d, ((uint64_t)DESC_HI << 32) | (lo_a + 2 * k), ((uint64_t)DESC_HI << 32) | (lo_b + 2 * k),
+                              idesc, (kb | k) != 0);
             }
-            umma_commit_cg<CG>(&empty_bar[s]);  // smem slot reusable (in both CTAs) once these MMAs retire
-            if (kb == num_kb - 1) umma_commit_cg<CG>(&tmem_full[acc]);  // accumulator complete (both CTAs' epilogues)
+            umma_commit_cg2(&empty_bar[s]);  // smem slot reusable (in both CTAs) once these MMAs retire
+            if (kb == num_kb - 1) umma_commit_cg2(&tmem_full[acc]);  // accumulator complete (both CTAs' epilogues)
           }
           __syncwarp();
         }
@@ -239,115 +227,155 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp >= EPI_WARP0) {
     // ------------------------------- epilogue (every CTA, its own 128 rows) -----------------
     const int ew = warp - EPI_WARP0;
-    const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..255
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the only ones this warp may touch
-    const int half = ew >> 2;      // column half of the tile
-    const int chunks = p.block_n / 32;
-    const int c_begin = half * ((chunks + 1) / 2);
-    const int c_end = half ? chunks : (chunks + 1) / 2;
-    const bool vec_ok = (p.ldc % 4 == 0) && (p.res_dtype < 0 || p.ldres % 4 == 0);
-    float* stg = staging + ew * 1024;
-    const int crow = lane >> 3, cch = lane & 7;  // coalesced layout: row-in-group and 16 B column chunk of this lane
-    uint32_t it = 0;
-    for (int tile = group; tile < num_tiles; tile += num_groups, ++it) {
-      const uint32_t acc = it & 1, acc_ph = (it >> 1) & 1;
-      const int m0 = (tile / p.tiles_n) * (BM * CG) + rank * BM + quarter * 32;
-      const int n0 = (tile % p.tiles_n) * p.block_n;
-      // stage this tile's bias slice in smem while the MMAs run
-      epi_bar_sync();  // everyone is done reading the previous tile's slice
-      if (et < p.block_n) bias_s[et] = (p.bias && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
-      epi_bar_sync();
-      mbar_wait(&tmem_full[acc], acc_ph);
-      tc_fence_after();
-      for (int c = c_begin; c < c_end; ++c) {
-        const int nb = n0 + c * 32;
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN_MAX + c * 32, r);
-        tmem_ld_wait();
-        if (nb >= p.N) continue;  // warp-uniform
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(bias_s + c * 32 + j);
-          float4 v = make_float4(__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y,
-                                 __uint_as_float(r[j + 2]) + b.z, __uint_as_float(r[j + 3]) + b.w);
-          if (p.act) {
-            v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
-            v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
-          }
-          *reinterpret_cast<float4*>(stg + lane * 32 + ((((j >> 2) ^ (lane & 7))) << 2)) = v;
+    const int quarter = warp & 3;   // TMEM lanes [32*quarter, +32) are the only ones this warp may touch
+    const int part = ew >> 2;       // this warp takes the chunks g == part (mod EPI_PARTS) of the CTA's chunk sequence
+    const int chunks = p.block_n >> 5;
+    const int my_tiles = (num_tiles - group + num_groups - 1) / num_groups;
+    const int total = my_tiles * chunks;
+    uint8_t* bufs = smem_epi + ew * (EPI_NBUF * EPI_BUF_BYTES);
+    uint64_t* rbar = res_full + ew * EPI_NBUF;
+    // byte offset of 16 B slot j of this thread's row inside a staging buffer, TMA swizzle applied:
+    //   fp32: 128 B rows, SWIZZLE_128B: slot j -> j ^ (row & 7);   bf16: 64 B rows, SWIZZLE_64B: slot j -> j ^ ((row >> 1) & 3)
+    const uint32_t row_base = OUT_BF16 ? lane * 64u : lane * 128u;
+    const uint32_t swz = OUT_BF16 ? ((lane >> 1) & 3u) : (lane & 7u);
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+
+    // (tile row0, column0) of sequence element g
+    auto chunk_coords = [&](int g, int& m0, int& n0) {
+      const int ti = g / chunks, c = g - ti * chunks;
+      const int tile = group + ti * num_groups;
+      m0 = (tile / p.tiles_n) * (BM * CG) + rank * BM + quarter * 32;
+      n0 = (tile % p.tiles_n) * p.block_n + c * 32;
+    };
+    if (RES) {
+      if (part < total) {
+        int m0, n0;
+        chunk_coords(part, m0, n0);
+        if (n0 < p.N && m0 < p.M && elect_one()) {
+          mbar_arrive_expect_tx(&rbar[0], 32 * 32 * 4);
+          tma_load_2d(bufs, &tmap_r, &rbar[0], n0, m0);
         }
         __syncwarp();
-        const int n = nb + cch * 4;
-        const bool vec = vec_ok && n + 4 <= p.N;
-        float4 v[8];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int row = g * 4 + crow;
-          v[g] = *reinterpret_cast<const float4*>(stg + row * 32 + ((cch ^ (row & 7)) << 2));
-        }
-        if (!(p.debug & 1) && n < p.N) {
-          if (vec) {
-            // all residual loads first (the in-place residual aliases C, so the compiler may not hoist them itself)
-            if (p.res_dtype == MVLT_F32) {
-              float4 t[8];
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const int m = m0 + g * 4 + crow;
-                t[g] = m < p.M ? load4(reinterpret_cast<const float*>(p.res) + (long long)m * p.ldres + n) : make_float4(0, 0, 0, 0);
-              }
-#pragma unroll
-              for (int g = 0; g < 8; ++g) { v[g].x += t[g].x; v[g].y += t[g].y; v[g].z += t[g].z; v[g].w += t[g].w; }
-            } else if (p.res_dtype == MVLT_BF16) {
-              float4 t[8];
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const int m = m0 + g * 4 + crow;
-                t[g] = m < p.M ? load4(reinterpret_cast<const bf16*>(p.res) + (long long)m * p.ldres + n) : make_float4(0, 0, 0, 0);
-              }
-#pragma unroll
-              for (int g = 0; g < 8; ++g) { v[g].x += t[g].x; v[g].y += t[g].y; v[g].z += t[g].z; v[g].w += t[g].w; }
-            }
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const int m = m0 + g * 4 + crow;
-              if (m >= p.M) continue;
-              if (p.out_dtype == MVLT_F32) store4(reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + n, v[g]);
-              else store4(reinterpret_cast<bf16*>(p.C) + (long long)m * p.ldc + n, v[g]);
-            }
-          } else {
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const int m = m0 + g * 4 + crow;
-              if (m >= p.M) continue;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                if (n + q >= p.N) break;
-                float x = q == 0 ? v[g].x : q == 1 ? v[g].y : q == 2 ? v[g].z : v[g].w;
-                const long long ro = (long long)m * p.ldres + n + q, co = (long long)m * p.ldc + n + q;
-                if (p.res_dtype == MVLT_F32) x += reinterpret_cast<const float*>(p.res)[ro];
-                else if (p.res_dtype == MVLT_BF16) x += to_f32(reinterpret_cast<const bf16*>(p.res)[ro]);
-                if (p.out_dtype == MVLT_F32) reinterpret_cast<float*>(p.C)[co] = x;
-                else reinterpret_cast<bf16*>(p.C)[co] = __float2bfloat16_rn(x);
-              }
-            }
-          }
-        }
-        __syncwarp();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG == 2) mbar_arrive_remote(&tmem_empty[acc], 0);
-        else mbar_arrive(&tmem_empty[acc]);
       }
     }
+    int cur_ti = -1;  // tile iteration whose accumulator this warp currently holds
+    auto release_tile = [&](int ti) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tmem_empty[ti & 1], 0);
+    };
+    auto acquire_tile = [&](int ti) {
+      mbar_wait(&tmem_full[ti & 1], (ti >> 1) & 1);
+      tc_fence_after();
+    };
+    int k = 0;
+    uint32_t res_parity = 0;  // bit b: parity of the next residual load to land in staging buffer b
+    for (int g = part; g < total; g += EPI_PARTS, ++k) {
+      const int ti = g / chunks, c = g - ti * chunks;
+      const int buf = k % EPI_NBUF;
+      uint8_t* sb = bufs + buf * EPI_BUF_BYTES;
+      int m0, n0;
+      chunk_coords(g, m0, n0);
+      const bool live = n0 < p.N && m0 < p.M;  // warp-uniform: the chunk holds at least one real element
+      // at most the store of step k-1 is still reading shared memory.  3 buffers (RES): buffer (k+1) % 3, last used by
+      // step k-2, is free for the next residual chunk; 2 buffers: buffer k % 2 (step k-2) is free for this step's writes
+      if (elect_one()) {
+        bulk_wait_read<1>();
+        if (RES && g + EPI_PARTS < total) {
+          int m1, n1;
+          chunk_coords(g + EPI_PARTS, m1, n1);
+          if (n1 < p.N && m1 < p.M) {
+            const int nb = (k + 1) % EPI_NBUF;
+            mbar_arrive_expect_tx(&rbar[nb], 32 * 32 * 4);
+            tma_load_2d(bufs + nb * EPI_BUF_BYTES, &tmap_r, &rbar[nb], n1, m1);
+          }
+        }
+      }
+      __syncwarp();
+      while (cur_ti < ti) {  // also passes through tiles in which this warp owns no chunk (block_n = 32)
+        if (cur_ti >= 0) release_tile(cur_ti);
+        ++cur_ti;
+        acquire_tile(cur_ti);
+      }
+      if (live) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_lane + (uint32_t)((ti & 1) * BN_MAX + c * 32), r);
+        if (RES) {
+          mbar_wait(&rbar[buf], (res_parity >> buf) & 1);
+          res_parity ^= 1u << buf;
+        }
+        tmem_ld_wait();
+        float2 v[16];  // this thread's row: 32 consecutive columns as 16 packed pairs
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+        if (p.bias != nullptr) {
+          if (n0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+              v[2 * j] = add2(v[2 * j], make_float2(b.x, b.y));
+              v[2 * j + 1] = add2(v[2 * j + 1], make_float2(b.z, b.w));
+            }
+          } else {  // ragged N edge
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int n = n0 + 2 * i;
+              v[i].x += n < p.N ? __ldg(p.bias + n) : 0.f;
+              v[i].y += n + 1 < p.N ? __ldg(p.bias + n + 1) : 0.f;
+            }
+          }
+        }
+        if (ACT == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = gelu_erf_fast2(v[i]);
+        } else if (ACT == 2) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = make_float2(tanhf(v[i].x), tanhf(v[i].y));
+        }
+        if (OUT_BF16) {
+          // 8 bf16 (4 pairs) per 16 B slot
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(sb + row_base + (((uint32_t)j ^ swz) << 4)) =
+                make_uint4(pack_bf16x2(v[4 * j].x, v[4 * j].y), pack_bf16x2(v[4 * j + 1].x, v[4 * j + 1].y),
+                           pack_bf16x2(v[4 * j + 2].x, v[4 * j + 2].y), pack_bf16x2(v[4 * j + 3].x, v[4 * j + 3].y));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4* slot = reinterpret_cast<float4*>(sb + row_base + (((uint32_t)j ^ swz) << 4));
+            float2 a = v[2 * j], b = v[2 * j + 1];
+            if (RES) {
+              const float4 t = *slot;
+              a = add2(a, make_float2(t.x, t.y));
+              b = add2(b, make_float2(t.z, t.w));
+            }
+            *slot = make_float4(a.x, a.y, b.x, b.y);
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA unit
+      }
+      __syncwarp();
+      if (elect_one()) {
+        if (live) tma_store_2d(&tmap_c, sb, n0, m0);
+        bulk_commit();  // one group per step (empty when the chunk lies beyond N) keeps the wait_group arithmetic uniform
+      }
+      __syncwarp();
+    }
+    while (cur_ti < my_tiles - 1) {
+      if (cur_ti >= 0) release_tile(cur_ti);
+      ++cur_ti;
+      acquire_tile(cur_ti);
+    }
+    if (cur_ti >= 0) release_tile(cur_ti);
+    if (elect_one()) bulk_wait_all();  // all of this warp's stores have left shared memory and are globally performed
+    __syncwarp();
   }
 
   tc_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc_cg<CG>(tmem_base, TMEM_COLS);
+    tmem_dealloc_cg2(tmem_base, TMEM_COLS);
   }
 }
 
@@ -356,8 +384,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 static int g_num_sms = 0;
-static int g_ctas = 2;
-static int g_debug = 0;
+
+typedef void (*GemmKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, GemmParams);
+
+static int smem_bytes(bool out_bf16, bool res) {
+  return out_bf16 ? Plan<true, false>::SMEM_BYTES : res ? Plan<false, true>::SMEM_BYTES : Plan<false, false>::SMEM_BYTES;
+}
+
+static GemmKernel pick_kernel(int act, bool out_bf16, bool res) {
+#define MVLT_K(A, O, R) gemm_tc_kernel<A, O, R>
+  if (out_bf16) {
+    switch (act) {
+      case 0: return MVLT_K(0, true, false);
+      case 1: return MVLT_K(1, true, false);
+      default: return MVLT_K(2, true, false);
+    }
+  }
+  if (res) {
+    switch (act) {
+      case 0: return MVLT_K(0, false, true);
+      case 1: return MVLT_K(1, false, true);
+      default: return MVLT_K(2, false, true);
+    }
+  }
+  switch (act) {
+    case 0: return MVLT_K(0, false, false);
+    case 1: return MVLT_K(1, false, false);
+    default: return MVLT_K(2, false, false);
+  }
+#undef MVLT_K
+}
 
 static int gemm_tc_init() {
   if (g_encode) return MVLT_OK;
@@ -365,34 +421,38 @@ static int gemm_tc_init() {
   cudaDriverEntryPointQueryResult q;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
   if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return MVLT_ERR_DRIVER;
-  e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-  if (e != cudaSuccess) return (int)e;
+  for (int act = 0; act < 3; ++act)
+    for (int o = 0; o < 2; ++o)
+      for (int r = 0; r < 2; ++r) {
+        if (o && r) continue;
+        e = cudaFuncSetAttribute(pick_kernel(act, o != 0, r != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(o != 0, r != 0));
+        if (e != cudaSuccess) return (int)e;
+      }
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  if (const char* s = getenv("MVLT_GEMM_CTAS")) g_ctas = atoi(s) == 1 ? 1 : 2;
-  if (const char* s = getenv("MVLT_GEMM_DEBUG")) g_debug = atoi(s);
   g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   return MVLT_OK;
 }
 
-static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld_elems, int box_rows) {
+// 2-D row-major tensor map: dims {cols, rows}, row stride ld_elems, box {box_cols, box_rows}
+static int make_tmap(CUtensorMap* map, CUtensorMapDataType dt, int elt_bytes, const void* ptr, long long rows, long long cols,
+                     long long ld_elems, int box_cols, int box_rows, CUtensorMapSwizzle swz, CUtensorMapL2promotion promo) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld_elems * elt_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = g_encode(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MVLT_OK : MVLT_ERR_DRIVER;
 }
 
-// Tile-width heuristic: maximise (useful columns / padded columns) x (wave quantisation) x (smem-feed efficiency).
-static int pick_block_n(int M, int N, int groups, int cg) {
+// Tile-width heuristic.  Per 64-wide k-block a CTA moves 16 KB of A and 64*BN bytes of W through shared memory twice
+// (TMA fill + tensor-core read) for 2*BN tensor cycles, so the operand feed costs (16384/BN + 64) B per tensor cycle:
+// wide tiles win even when they quantise worse over the 74 CTA pairs (measured: profiles/r01_gemm_sweep_v3.log).
+static int pick_block_n(int M, int N, int K, int groups) {
   const int cand[] = {256, 192, 128, 96, 64, 32};
-  const int tiles_m = (M + BM * cg - 1) / (BM * cg);
+  const int tiles_m = (M + BM * CG - 1) / (BM * CG);
   double best = -1;
   int best_bn = 128;
   for (int bn : cand) {
@@ -401,34 +461,15 @@ static int pick_block_n(int M, int N, int groups, int cg) {
     const long long tiles = (long long)tiles_m * tn;
     const long long waves = (tiles + groups - 1) / groups;
     const double wave_eff = (double)tiles / ((double)waves * groups);
-    // tensor cycles per K=16 step vs cycles to read this CTA's operand slices from smem at 128 B/clk
-    const double mma_cycles = bn / 2.0;
-    const double feed = mma_cycles / ((4096.0 + (bn / cg) * 32.0) / 128.0);
-    const double score = useful * wave_eff * (feed < 1.0 ? feed : 1.0);
+    // short-K call sites are bound by their epilogue / HBM traffic, not by the operand feed: discount it
+    const double feed = pow(128.0 / (16384.0 / bn + 64.0), K >= 768 ? 1.0 : K / 768.0);
+    const double score = useful * wave_eff * feed;
     if (score > best + 1e-9) {
       best = score;
       best_bn = bn;
     }
   }
   return best_bn;
-}
-
-template <int CG>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t stream) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<CG>, ta, tb, p);
-  return e == cudaSuccess ? MVLT_OK : (int)e;
 }
 
 }  // namespace mvlt
@@ -442,28 +483,57 @@ extern "C" int mvlt_gemm_bf16_tc(const void* A, long long lda, const void* W, lo
                                  int K, int act, int out_dtype, int block_n, cudaStream_t stream) {
   if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0) return MVLT_ERR_INVALID;
   if (K % 16 != 0 || lda % 8 != 0 || ldw % 8 != 0) return MVLT_ERR_INVALID;  // TMA: 16 B aligned rows
-  if (((uintptr_t)A & 15) || ((uintptr_t)W & 15)) return MVLT_ERR_INVALID;
+  if (((uintptr_t)A & 15) || ((uintptr_t)W & 15) || ((uintptr_t)C & 15)) return MVLT_ERR_INVALID;
   if (act < 0 || act > 2 || (out_dtype != MVLT_F32 && out_dtype != MVLT_BF16)) return MVLT_ERR_INVALID;
-  if (!residual) res_dtype = -1;
-  if (res_dtype > MVLT_BF16) return MVLT_ERR_INVALID;
+  const bool out_bf16 = out_dtype == MVLT_BF16;
+  if (ldc % (out_bf16 ? 8 : 4) != 0) return MVLT_ERR_INVALID;                // TMA store: 16 B aligned rows
+  if (bias && ((uintptr_t)bias & 15)) return MVLT_ERR_INVALID;
+  const bool res = residual != nullptr;
+  if (res) {
+    // the fused residual is the fp32 residual stream of the model (Swin proj/fc2 in place, BERT attention/FFN outputs)
+    if (res_dtype != MVLT_F32 || out_bf16) return MVLT_ERR_UNSUPPORTED;
+    if (ldres % 4 != 0 || ((uintptr_t)residual & 15)) return MVLT_ERR_INVALID;
+  }
   int rc = gemm_tc_init();
   if (rc != MVLT_OK) return rc;
-  const int cg = g_ctas;
-  const int groups = g_num_sms / cg;
-  if (block_n <= 0) block_n = pick_block_n(M, N, groups, cg);
+  const int groups = g_num_sms / CG;
+  if (block_n <= 0) block_n = pick_block_n(M, N, K, groups);
   if (block_n % 32 != 0 || block_n > BN_MAX) return MVLT_ERR_INVALID;
 
-  CUtensorMap ta, tb;
-  if ((rc = make_tmap(&ta, A, M, K, lda, BM)) != MVLT_OK) return rc;
-  if ((rc = make_tmap(&tb, W, N, K, ldw, block_n / cg)) != MVLT_OK) return rc;
+  CUtensorMap ta, tb, tc, tr;
+  const CUtensorMapDataType cdt = out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapSwizzle cswz = out_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  if ((rc = make_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, M, K, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != MVLT_OK) return rc;
+  if ((rc = make_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, N, K, ldw, BK, block_n / CG, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != MVLT_OK) return rc;
+  if ((rc = make_tmap(&tc, cdt, out_bf16 ? 2 : 4, C, M, N, ldc, 32, 32, cswz, CU_TENSOR_MAP_L2_PROMOTION_NONE)) != MVLT_OK) return rc;
+  if (res) {
+    if ((rc = make_tmap(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, residual, M, N, ldres, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) != MVLT_OK) return rc;
+  } else {
+    tr = tc;
+  }
 
   GemmParams p;
-  p.C = C; p.ldc = ldc; p.bias = bias; p.res = residual; p.ldres = ldres;
-  p.M = M; p.N = N; p.K = K; p.block_n = block_n; p.act = act; p.out_dtype = out_dtype; p.res_dtype = res_dtype;
-  p.tiles_m = (M + BM * cg - 1) / (BM * cg);
+  p.bias = bias; p.M = M; p.N = N; p.K = K; p.block_n = block_n;
+  p.tiles_m = (M + BM * CG - 1) / (BM * CG);
   p.tiles_n = (N + block_n - 1) / block_n;
-  p.debug = g_debug;
   const int tiles = p.tiles_m * p.tiles_n;
-  const int grid = cg * (tiles < groups ? tiles : groups);
-  return cg == 2 ? launch<2>(ta, tb, p, grid, stream) : launch<1>(ta, tb, p, grid, stream);
+  const int grid = CG * (tiles < groups ? tiles : groups);
+
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes(out_bf16, res);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, pick_kernel(act, out_bf16, res), ta, tb, tc, tr, p);
+  return e == cudaSuccess ? MVLT_OK : (int)e;
 }

@@ -54,21 +54,56 @@ def test_gemm_tc_block_n(cuda, block_n):
 
 
 @pytest.mark.parametrize("act", [0, 1, 2])
-@pytest.mark.parametrize("res", [None, torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("res", [None, torch.float32])
 @pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
 def test_gemm_tc_epilogues(cuda, act, res, out_dtype):
-    from medical_vision_langauge_transformer_b200 import ops
+    from medical_vision_langauge_transformer_b200 import _lib, ops
     M, N, K = 1000, 768, 384
     a = rnd(M, K, seed=5).bfloat16()
     w = rnd(N, K, seed=6, scale=1 / math.sqrt(K)).bfloat16()
     bias = rnd(N, seed=7)
     r = None if res is None else rnd(M, N, seed=8).to(res)
+    if r is not None and out_dtype == torch.bfloat16:
+        # the fused residual is the model's fp32 residual stream: fp32 in, fp32 out; anything else is rejected, not emulated
+        with pytest.raises(_lib.MvltNativeError):
+            ops.linear(a, w, bias, act=act, residual=r, out_dtype=out_dtype)
+        return
     out = ops.linear(a, w, bias, act=act, residual=r, out_dtype=out_dtype)
     ref = a.float() @ w.float().t() + bias
     ref = F.gelu(ref) if act == 1 else torch.tanh(ref) if act == 2 else ref
     if r is not None:
         ref = ref + r.float()
     assert relerr(out, ref) < (1e-2 if out_dtype == torch.bfloat16 else 2e-3)
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(300, 96, 96, 0), (300, 96, 96, 32), (517, 192, 768, 64), (262, 768, 3072, 0),
+                                      (1000, 288, 96, 192), (130, 1000, 64, 0), (6272, 384, 1536, 128)])
+def test_gemm_tc_residual_ragged_and_tile_widths(cuda, M, N, K, bn):
+    """fp32 residual epilogue (TMA-prefetched chunks, in place and out of place) at ragged M/N edges and with tile
+    widths whose chunk count does not divide evenly among the epilogue warps."""
+    from medical_vision_langauge_transformer_b200 import ops
+    a = rnd(M, K, seed=21).bfloat16()
+    w = rnd(N, K, seed=22, scale=1 / math.sqrt(K)).bfloat16()
+    bias = rnd(N, seed=23)
+    x = rnd(M, N, seed=24)
+    ref = x + a.float() @ w.float().t() + bias
+    out = ops.linear(a, w, bias, residual=x, out_dtype=torch.float32, block_n=bn)      # out of place (BERT)
+    assert relerr(out, ref) < 2e-3
+    ops.linear(a, w, bias, residual=x, out=x, block_n=bn)                               # in place (Swin)
+    assert relerr(x, ref) < 2e-3
+    g = ops.linear(a, w, bias, act=1, out_dtype=torch.bfloat16, block_n=bn)             # bf16 + GELU, same shapes
+    assert relerr(g, F.gelu(a.float() @ w.float().t() + bias)) < 1e-2
+
+
+def test_gemm_tc_gelu_accuracy(cuda):
+    """The packed-math erf-GELU epilogue against torch's exact erf GELU in fp32 output: abs error ~1e-6 + GEMM rounding."""
+    from medical_vision_langauge_transformer_b200 import ops
+    M, N, K = 512, 256, 64
+    a = (rnd(M, K, seed=31) * 3).bfloat16()
+    w = rnd(N, K, seed=32, scale=0.25).bfloat16()
+    out = ops.linear(a, w, act=1, out_dtype=torch.float32)
+    pre = a.float() @ w.float().t()
+    assert (out - F.gelu(pre)).abs().max().item() < 2e-5 * max(1.0, pre.abs().max().item())
 
 
 def test_gemm_tc_inplace_residual_and_strided_a(cuda):
