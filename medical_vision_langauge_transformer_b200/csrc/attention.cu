@@ -65,153 +65,293 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint3
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// grid = (groups, heads); block = 32 * NPAD/16 (one 16-row query tile per warp)
-template <int HD, int NPAD, bool WINDOW>
-__global__ void __launch_bounds__(NPAD * 2)
-attn_mma_kernel(const AttnParams p) {
-  constexpr int LDS = HD + 8;  // padded row (bf16 elements): conflict-free ldmatrix
-  constexpr int NT = NPAD / 8; // key tiles of 8
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float NEG_BIG = -1.0e30f;  // "minus infinity" that stays finite through (x - max) and scale multiplies
+
+// ---- Swin window attention, bf16: ONE WARP per (image, window, head) ------------------------------------------------
+// The 49x32 q, k, v slices of the item are cp.async'ed into this warp's private 15 KB of shared memory (rows found
+// through the roll/partition index map, computed once per item), K fragments are held in registers across the four
+// 16-row query tiles, the score accumulators are INITIALISED with (rel-pos bias + shift mask) / scale so that
+// exp2(scale*log2e * acc - max) needs one FFMA + one MUFU per score, and P.V runs from the S fragments in registers.
+// No __syncthreads anywhere: the four warps of a CTA are independent pipelines (loads of one overlap math of another).
+constexpr int WA_LDS = 40;                                   // padded row (bf16 elements): conflict-free ldmatrix
+constexpr int WA_MAT = 64 * WA_LDS;                          // elements per staged matrix
+constexpr int WA_WARP_BYTES = 3 * WA_MAT * 2 + 64 * 4 + 64 * 4;  // Q,K,V + row index table + region ids
+constexpr int WA_WARPS = 4;
+
+struct WinParams {
+  const bf16* qkv;
+  bf16* out;
+  const float* relbias;  // [heads, 64, 64] fp32, zero padded
+  int H, W, C, heads, shift, n_items, nWh, nWw;
+  float scale;
+};
+
+__global__ void __launch_bounds__(WA_WARPS * 32)
+window_attn_warp_kernel(const WinParams p) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  bf16* Qs = reinterpret_cast<bf16*>(smem_attn + warp * WA_WARP_BYTES);
+  bf16* Ks = Qs + WA_MAT;
+  bf16* Vs = Ks + WA_MAT;
+  int* rowoff = reinterpret_cast<int*>(Vs + WA_MAT);   // token i of this window -> row of the [B*H*W, .] matrices
+  float* regf = reinterpret_cast<float*>(rowoff + 64);  // region id of token i in the shifted image (vfe.py:321-339)
+  // padding rows (tokens 49..63) are zero for the whole kernel: loads only ever touch rows 0..48
+  for (int i = lane; i < 3 * WA_MAT / 8; i += 32) reinterpret_cast<uint4*>(Qs)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = lane; i < 64; i += 32) { rowoff[i] = 0; regf[i] = 0.f; }
+  __syncwarp();
+
+  const int nW = p.nWh * p.nWw;
+  const long long ld_qkv = 3LL * p.C, ld_out = p.C;
+  const float inv_scale = 1.0f / p.scale, c = p.scale * LOG2E;
+  for (int item = blockIdx.x * WA_WARPS + warp; item < p.n_items; item += gridDim.x * WA_WARPS) {
+    const int head = item % p.heads, wg = item / p.heads;
+    const int b = wg / nW, w = wg - b * nW;
+    const int wh = w / p.nWw, ww = w - wh * p.nWw;
+    const int cls = p.shift > 0 ? ((wh == p.nWh - 1 ? 2 : 0) | (ww == p.nWw - 1 ? 1 : 0)) : 0;
+    for (int i = lane; i < 49; i += 32) {
+      const int r = i / 7, cc = i - r * 7;
+      int h = wh * 7 + r + p.shift, x = ww * 7 + cc + p.shift;   // torch.roll(-shift) then partition == read at +shift
+      if (h >= p.H) h -= p.H;
+      if (x >= p.W) x -= p.W;
+      rowoff[i] = (b * p.H + h) * p.W + x;
+      const int rh = (cls & 2) ? (r < 7 - p.shift ? 1 : 2) : 0, rw = (cls & 1) ? (cc < 7 - p.shift ? 1 : 2) : 0;
+      regf[i] = (float)(rh * 3 + rw);
+    }
+    __syncwarp();
+    {  // 49 rows x (4 q + 4 k + 4 v) 16-byte chunks: 16 lanes per row, 2 rows per pass
+      const int ch = lane & 15, which = ch >> 2, c4 = ch & 3;
+      const bf16* src0 = p.qkv + (long long)which * p.C + head * 32 + c4 * 8;
+      bf16* dst0 = Qs + which * WA_MAT + c4 * 8;
+      if (ch < 12) {
+#pragma unroll 5
+        for (int it = 0; it < 25; ++it) {
+          const int row = 2 * it + (lane >> 4);
+          if (row < 49) cp_async16(dst0 + row * WA_LDS, src0 + (long long)rowoff[row] * ld_qkv);
+        }
+      }
+      cp_async_wait_all();
+    }
+    __syncwarp();
+
+    uint32_t kf[7][4];  // B fragments of K^T for key tiles 0..6 (keys 0..55), both k-steps of the 32-wide head
+#pragma unroll
+    for (int nt = 0; nt < 7; ++nt)
+      ldsm_x4(smem_u32(Ks + (nt * 8 + (lane & 7)) * WA_LDS + (lane >> 3) * 8), kf[nt][0], kf[nt][1], kf[nt][2], kf[nt][3]);
+    const float* rb = p.relbias + (long long)head * 4096;
+
+#pragma unroll 1
+    for (int mt = 0; mt < 4; ++mt) {
+      const int r0 = mt * 16, i0 = r0 + g, i1 = r0 + g + 8;
+      uint32_t qa[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        ldsm_x4(smem_u32(Qs + (r0 + (lane & 15)) * WA_LDS + ks * 16 + (lane >> 4) * 8), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+      float s[7][4];
+      const float ri0 = regf[i0], ri1 = regf[i1];
+#pragma unroll
+      for (int nt = 0; nt < 7; ++nt) {
+        const int j = nt * 8 + 2 * t;
+        float2 b0 = __ldg(reinterpret_cast<const float2*>(rb + i0 * 64 + j));
+        float2 b1 = __ldg(reinterpret_cast<const float2*>(rb + i1 * 64 + j));
+        if (cls) {  // warp-uniform: only windows on the last window row / column carry the -100 shift mask
+          const float2 rj = *reinterpret_cast<const float2*>(regf + j);
+          b0.x += rj.x != ri0 ? -100.f : 0.f; b0.y += rj.y != ri0 ? -100.f : 0.f;
+          b1.x += rj.x != ri1 ? -100.f : 0.f; b1.y += rj.y != ri1 ? -100.f : 0.f;
+        }
+        s[nt][0] = b0.x * inv_scale; s[nt][1] = b0.y * inv_scale;
+        s[nt][2] = b1.x * inv_scale; s[nt][3] = b1.y * inv_scale;
+      }
+      // keys 49..55 do not exist: key 48 is column 0 of the pair held by t == 0 in tile 6
+      s[6][1] = NEG_BIG; s[6][3] = NEG_BIG;
+      if (t != 0) { s[6][0] = NEG_BIG; s[6][2] = NEG_BIG; }
+#pragma unroll
+      for (int nt = 0; nt < 7; ++nt) {
+        mma_bf16_16816(s[nt], qa[0][0], qa[0][1], qa[0][2], qa[0][3], kf[nt][0], kf[nt][1]);
+        mma_bf16_16816(s[nt], qa[1][0], qa[1][1], qa[1][2], qa[1][3], kf[nt][2], kf[nt][3]);
+      }
+      float mx0 = s[0][0], mx1 = s[0][2];
+#pragma unroll
+      for (int nt = 0; nt < 7; ++nt) {
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float m0c = -mx0 * c, m1c = -mx1 * c;
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 7; ++nt) {
+        s[nt][0] = ex2_approx(fmaf(s[nt][0], c, m0c)); s[nt][1] = ex2_approx(fmaf(s[nt][1], c, m0c));
+        s[nt][2] = ex2_approx(fmaf(s[nt][2], c, m1c)); s[nt][3] = ex2_approx(fmaf(s[nt][3], c, m1c));
+        sum0 += s[nt][0] + s[nt][1];
+        sum1 += s[nt][2] + s[nt][3];
+      }
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+
+      float o[4][4];
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint32_t a0 = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+        const uint32_t a1 = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+        const uint32_t a2 = kk < 3 ? pack_bf16x2(s[kk < 3 ? 2 * kk + 1 : 0][0], s[kk < 3 ? 2 * kk + 1 : 0][1]) : 0u;  // keys 56..63: P = 0
+        const uint32_t a3 = kk < 3 ? pack_bf16x2(s[kk < 3 ? 2 * kk + 1 : 0][2], s[kk < 3 ? 2 * kk + 1 : 0][3]) : 0u;
+#pragma unroll
+        for (int dp = 0; dp < 2; ++dp) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_t(smem_u32(Vs + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * WA_LDS + dp * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
+          mma_bf16_16816(o[2 * dp], a0, a1, a2, a3, b0, b1);
+          mma_bf16_16816(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
+        }
+      }
+      // normalise and park the tile in its own Q rows (already in registers); rows >= 49 stay zero
+      const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+      __syncwarp();
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn) {
+        if (i0 < 49) *reinterpret_cast<uint32_t*>(Qs + i0 * WA_LDS + dn * 8 + 2 * t) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
+        if (i1 < 49) *reinterpret_cast<uint32_t*>(Qs + i1 * WA_LDS + dn * 8 + 2 * t) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
+      }
+    }
+    __syncwarp();
+    {  // window_reverse + roll back == scatter through the same index map: 49 rows x 4 chunks of 16 B
+      bf16* dst0 = p.out + head * 32 + (lane & 3) * 8;
+#pragma unroll
+      for (int it = 0; it < 7; ++it) {
+        const int row = it * 8 + (lane >> 2);
+        if (row < 49)
+          *reinterpret_cast<uint4*>(dst0 + (long long)rowoff[row] * ld_out) = *reinterpret_cast<const uint4*>(Qs + row * WA_LDS + (lane & 3) * 8);
+      }
+    }
+    __syncwarp();  // the next item rewrites rowoff / Q / K / V
+  }
+}
+
+// ---- BERT joint attention, bf16: one CTA per (sample, head), one 16-row query tile per warp --------------------------
+// grid = (B, heads); block = 32 * NPAD/16.  Q/K/V rows are cp.async'ed into padded shared memory; the score
+// accumulators start from (additive key mask | seq2seq mask) / scale; exp2 with the scale folded in; P.V from registers.
+template <int NPAD>
+__global__ void __launch_bounds__(NPAD * 2, NPAD > 96 ? 2 : 3)
+joint_attn_kernel(const AttnParams p) {
+  constexpr int HD = 64, LDS = HD + 8, NT = NPAD / 8, CPR = HD / 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* Qs = reinterpret_cast<bf16*>(smem_attn);
   bf16* Ks = Qs + NPAD * LDS;
   bf16* Vs = Ks + NPAD * LDS;
-  float* aux = reinterpret_cast<float*>(Vs + NPAD * LDS);  // window: region ids, joint: key mask   [NPAD]
+  float* aux = reinterpret_cast<float*>(Vs + NPAD * LDS);  // [NPAD] additive key mask / scale (NEG_BIG beyond ntok)
 
   const int group = blockIdx.x, head = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bf16* qkv = reinterpret_cast<const bf16*>(p.qkv);
+  const bf16* qkv = reinterpret_cast<const bf16*>(p.qkv) + (long long)group * p.ntok * p.ld_qkv + head * HD;
+  const float inv_scale = 1.0f / p.scale, c = p.scale * LOG2E;
 
-  // ---- stage Q, K, V rows (16 B chunks), zero-fill the padding rows ----
-  constexpr int CPR = HD / 8;  // 16 B chunks per row per matrix
-  for (int idx = tid; idx < NPAD * 3 * CPR; idx += blockDim.x) {
+  for (int idx = tid; idx < NPAD * 3 * CPR; idx += NPAD * 2) {
     const int ch = idx % CPR, which = (idx / CPR) % 3, i = idx / (3 * CPR);
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (i < p.ntok) {
-      const long long row = token_row<WINDOW>(p, group, i);
-      val = *reinterpret_cast<const uint4*>(qkv + row * p.ld_qkv + which * p.C + head * HD + ch * 8);
-    }
-    bf16* dst = (which == 0 ? Qs : which == 1 ? Ks : Vs) + i * LDS + ch * 8;
-    *reinterpret_cast<uint4*>(dst) = val;
+    bf16* dst = Qs + which * (NPAD * LDS) + i * LDS + ch * 8;
+    if (i < p.ntok) cp_async16(dst, qkv + (long long)i * p.ld_qkv + which * p.C + ch * 8);
+    else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
   }
-  for (int i = tid; i < NPAD; i += blockDim.x) {
-    float a = 0.f;
-    if (i < p.ntok) {
-      if (WINDOW) a = p.shift > 0 ? (float)shift_region(p, group, i) : 0.f;
-      else a = p.kmask[(long long)group * p.ntok + i];
-    }
-    aux[i] = a;
-  }
+  for (int i = tid; i < NPAD; i += NPAD * 2)
+    aux[i] = i < p.ntok ? (p.seq2seq ? 0.f : p.kmask[(long long)group * p.ntok + i] * inv_scale) : NEG_BIG;
+  cp_async_wait_all();
   __syncthreads();
 
   const int g = lane >> 2, t = lane & 3;
-  const int r0 = warp * 16;  // first query row of this warp
-  if (r0 < p.ntok) {
-    // ---- S = Q K^T ----
-    uint32_t qa[HD / 16][4];
+  const int r0 = warp * 16;
+  if (r0 >= p.ntok) return;
+  const int i0 = r0 + g, i1 = r0 + g + 8;
+  float s[NT][4];
 #pragma unroll
-    for (int ks = 0; ks < HD / 16; ++ks)
-      ldsm_x4(smem_u32(Qs + (r0 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
-    float s[NT][4];
+  for (int nt = 0; nt < NT; ++nt) {
+    const int j = nt * 8 + 2 * t;
+    const float2 m = *reinterpret_cast<const float2*>(aux + j);
+    s[nt][0] = s[nt][2] = m.x;
+    s[nt][1] = s[nt][3] = m.y;
+    if (p.seq2seq) {  // model.py:118-123: text rows see the image block and the text up to themselves
+      const float blocked = -10000.f * inv_scale;
+      if (j > i0 && j > p.obj_end) s[nt][0] += blocked;
+      if (j + 1 > i0 && j + 1 > p.obj_end) s[nt][1] += blocked;
+      if (j > i1 && j > p.obj_end) s[nt][2] += blocked;
+      if (j + 1 > i1 && j + 1 > p.obj_end) s[nt][3] += blocked;
+    }
+  }
+#pragma unroll
+  for (int kq = 0; kq < HD / 32; ++kq) {
+    uint32_t qa[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+      ldsm_x4(smem_u32(Qs + (r0 + (lane & 15)) * LDS + kq * 32 + ks * 16 + (lane >> 4) * 8), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-#pragma unroll
-      for (int kq = 0; kq < HD / 32; ++kq) {
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4(smem_u32(Ks + (nt * 8 + (lane & 7)) * LDS + kq * 32 + (lane >> 3) * 8), b0, b1, b2, b3);
-        mma_bf16_16816(s[nt], qa[2 * kq][0], qa[2 * kq][1], qa[2 * kq][2], qa[2 * kq][3], b0, b1);
-        mma_bf16_16816(s[nt], qa[2 * kq + 1][0], qa[2 * kq + 1][1], qa[2 * kq + 1][2], qa[2 * kq + 1][3], b2, b3);
-      }
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4(smem_u32(Ks + (nt * 8 + (lane & 7)) * LDS + kq * 32 + (lane >> 3) * 8), b0, b1, b2, b3);
+      mma_bf16_16816(s[nt], qa[0][0], qa[0][1], qa[0][2], qa[0][3], b0, b1);
+      mma_bf16_16816(s[nt], qa[1][0], qa[1][1], qa[1][2], qa[1][3], b2, b3);
     }
-    // ---- scale, bias, mask; row softmax (rows r0+g and r0+g+8) ----
-    const int i0 = r0 + g, i1 = r0 + g + 8;
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-    float ra0 = 0.f, ra1 = 0.f;
-    const float* rb0 = nullptr;
-    const float* rb1 = nullptr;
-    if (WINDOW) {
-      ra0 = aux[i0]; ra1 = aux[i1];
-      rb0 = p.relbias + ((long long)head * 64 + i0) * 64;
-      rb1 = p.relbias + ((long long)head * 64 + i1) * 64;
-    }
+  }
+  float mx0 = s[0][0], mx1 = s[0][2];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const int j = nt * 8 + 2 * t;
+  for (int nt = 0; nt < NT; ++nt) {
+    mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+    mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  const float m0c = -mx0 * c, m1c = -mx1 * c;
+  float sum0 = 0.f, sum1 = 0.f;
+  uint32_t pk[NT][2];  // P as bf16 pairs: [nt][0] = row g, [nt][1] = row g+8
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int jj = j + e;
-        float add0, add1;
-        if (WINDOW) {
-          const float rj = aux[jj];
-          add0 = __ldg(rb0 + jj) + (rj != ra0 ? -100.f : 0.f);
-          add1 = __ldg(rb1 + jj) + (rj != ra1 ? -100.f : 0.f);
-        } else if (p.seq2seq) {
-          add0 = (jj <= i0 || jj <= p.obj_end) ? 0.f : -10000.f;
-          add1 = (jj <= i1 || jj <= p.obj_end) ? 0.f : -10000.f;
-        } else {
-          add0 = add1 = aux[jj];
-        }
-        const bool valid = jj < p.ntok;
-        s[nt][e] = valid ? s[nt][e] * p.scale + add0 : -INFINITY;
-        s[nt][2 + e] = valid ? s[nt][2 + e] * p.scale + add1 : -INFINITY;
-        mx0 = fmaxf(mx0, s[nt][e]);
-        mx1 = fmaxf(mx1, s[nt][2 + e]);
-      }
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    constexpr float LOG2E = 1.4426950408889634f;
-    float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        s[nt][e] = exp2f((s[nt][e] - mx0) * LOG2E);
-        s[nt][2 + e] = exp2f((s[nt][2 + e] - mx1) * LOG2E);
-        sum0 += s[nt][e];
-        sum1 += s[nt][2 + e];
-      }
-    }
-    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  for (int nt = 0; nt < NT; ++nt) {
+    const float p0 = ex2_approx(fmaf(s[nt][0], c, m0c)), p1 = ex2_approx(fmaf(s[nt][1], c, m0c));
+    const float p2 = ex2_approx(fmaf(s[nt][2], c, m1c)), p3 = ex2_approx(fmaf(s[nt][3], c, m1c));
+    sum0 += p0 + p1;
+    sum1 += p2 + p3;
+    pk[nt][0] = pack_bf16x2(p0, p1);
+    pk[nt][1] = pack_bf16x2(p2, p3);
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
 
-    // ---- O = P V ----
-    float o[HD / 8][4];
+  float o[HD / 8][4];
 #pragma unroll
-    for (int dn = 0; dn < HD / 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+  for (int dn = 0; dn < HD / 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < NPAD / 16; ++kk) {
-      const uint32_t a0 = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-      const uint32_t a1 = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-      const uint32_t a2 = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-      const uint32_t a3 = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+  for (int kk = 0; kk < NPAD / 16; ++kk) {
 #pragma unroll
-      for (int dp = 0; dp < HD / 16; ++dp) {
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4_t(smem_u32(Vs + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + dp * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
-        mma_bf16_16816(o[2 * dp], a0, a1, a2, a3, b0, b1);
-        mma_bf16_16816(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
-      }
+    for (int dp = 0; dp < HD / 16; ++dp) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(smem_u32(Vs + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + dp * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
+      mma_bf16_16816(o[2 * dp], pk[2 * kk][0], pk[2 * kk][1], pk[2 * kk + 1][0], pk[2 * kk + 1][1], b0, b1);
+      mma_bf16_16816(o[2 * dp + 1], pk[2 * kk][0], pk[2 * kk][1], pk[2 * kk + 1][0], pk[2 * kk + 1][1], b2, b3);
     }
-    // ---- normalise, park in this warp's own Q rows, then 16 B row-contiguous stores ----
-    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
-    __syncwarp();
+  }
+  const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+  __syncwarp();
 #pragma unroll
-    for (int dn = 0; dn < HD / 8; ++dn) {
-      *reinterpret_cast<uint32_t*>(Qs + (r0 + g) * LDS + dn * 8 + 2 * t) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
-      *reinterpret_cast<uint32_t*>(Qs + (r0 + g + 8) * LDS + dn * 8 + 2 * t) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
-    }
-    __syncwarp();
-    bf16* out = reinterpret_cast<bf16*>(p.out);
-    for (int idx = lane; idx < 16 * CPR; idx += 32) {
-      const int rr = idx / CPR, ch = idx % CPR;
-      const int i = r0 + rr;
-      if (i < p.ntok) {
-        const long long row = token_row<WINDOW>(p, group, i);
-        *reinterpret_cast<uint4*>(out + row * p.ld_out + head * HD + ch * 8) =
-            *reinterpret_cast<const uint4*>(Qs + i * LDS + ch * 8);
-      }
-    }
+  for (int dn = 0; dn < HD / 8; ++dn) {
+    *reinterpret_cast<uint32_t*>(Qs + i0 * LDS + dn * 8 + 2 * t) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
+    *reinterpret_cast<uint32_t*>(Qs + i1 * LDS + dn * 8 + 2 * t) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
+  }
+  __syncwarp();
+  bf16* out = reinterpret_cast<bf16*>(p.out) + (long long)group * p.ntok * p.ld_out + head * HD;
+  for (int idx = lane; idx < 16 * CPR; idx += 32) {
+    const int rr = idx / CPR, ch = idx % CPR;
+    const int i = r0 + rr;
+    if (i < p.ntok)
+      *reinterpret_cast<uint4*>(out + (long long)i * p.ld_out + ch * 8) = *reinterpret_cast<const uint4*>(Qs + i * LDS + ch * 8);
   }
 }
 
@@ -299,7 +439,8 @@ using namespace mvlt;
 
 extern "C" int mvlt_attn_init(void) {
   int rc;
-  if ((rc = set_smem(attn_mma_kernel<64, JOINT_NPAD, false>, 3 * JOINT_NPAD * 72 * 2 + JOINT_NPAD * 4)) != MVLT_OK) return rc;
+  if ((rc = set_smem(joint_attn_kernel<JOINT_NPAD>, 3 * JOINT_NPAD * 72 * 2 + JOINT_NPAD * 4)) != MVLT_OK) return rc;
+  if ((rc = set_smem(window_attn_warp_kernel, WA_WARPS * WA_WARP_BYTES)) != MVLT_OK) return rc;
   if ((rc = set_smem(attn_f32_kernel<64, false>, 200 * 1024)) != MVLT_OK) return rc;
   if ((rc = set_smem(attn_f32_kernel<32, true>, 64 * 1024)) != MVLT_OK) return rc;
   return MVLT_OK;
@@ -315,8 +456,16 @@ extern "C" int mvlt_window_attention(const void* qkv, void* out, int dtype, cons
   p.scale = scale; p.H = H; p.W = W; p.ws = window; p.shift = shift; p.relbias = relbias;
   dim3 grid(B * (H / window) * (W / window), heads);
   if (dtype == MVLT_BF16) {
-    constexpr int NPAD = 64;
-    attn_mma_kernel<32, NPAD, true><<<grid, NPAD * 2, 3 * NPAD * 40 * 2 + NPAD * 4, stream>>>(p);
+    WinParams wp;
+    wp.qkv = reinterpret_cast<const bf16*>(qkv); wp.out = reinterpret_cast<bf16*>(out); wp.relbias = relbias;
+    wp.H = H; wp.W = W; wp.C = C; wp.heads = heads; wp.shift = shift; wp.nWh = H / window; wp.nWw = W / window;
+    wp.n_items = B * wp.nWh * wp.nWw * heads; wp.scale = scale;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ctas = (wp.n_items + WA_WARPS - 1) / WA_WARPS;
+    const int gridx = ctas < 3 * sms ? ctas : 3 * sms;  // 3 CTAs (62 KB each) are resident per SM
+    window_attn_warp_kernel<<<gridx, WA_WARPS * 32, WA_WARPS * WA_WARP_BYTES, stream>>>(wp);
   } else if (dtype == MVLT_F32) {
     const int npad = 52;
     const int bytes = (3 * npad * 33 + npad + 49 * (npad + 1)) * 4;
@@ -338,9 +487,9 @@ extern "C" int mvlt_joint_attention(const void* qkv, void* out, int dtype, const
   dim3 grid(B, heads);
   if (dtype == MVLT_BF16) {
     if (S <= JOINT_NPAD_S)
-      attn_mma_kernel<64, JOINT_NPAD_S, false><<<grid, JOINT_NPAD_S * 2, 3 * JOINT_NPAD_S * 72 * 2 + JOINT_NPAD_S * 4, stream>>>(p);
+      joint_attn_kernel<JOINT_NPAD_S><<<grid, JOINT_NPAD_S * 2, 3 * JOINT_NPAD_S * 72 * 2 + JOINT_NPAD_S * 4, stream>>>(p);
     else if (S <= JOINT_NPAD)
-      attn_mma_kernel<64, JOINT_NPAD, false><<<grid, JOINT_NPAD * 2, 3 * JOINT_NPAD * 72 * 2 + JOINT_NPAD * 4, stream>>>(p);
+      joint_attn_kernel<JOINT_NPAD><<<grid, JOINT_NPAD * 2, 3 * JOINT_NPAD * 72 * 2 + JOINT_NPAD * 4, stream>>>(p);
     else return MVLT_ERR_UNSUPPORTED;
   } else if (dtype == MVLT_F32) {
     const int npad = (S + 3) & ~3;

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.ins
 import torch
 from medical_vision_langauge_transformer_b200 import ops, _lib
 ap = argparse.ArgumentParser(); ap.add_argument("--reps", type=int, default=10); ap.add_argument("--flush", action="store_true")
-ap.add_argument("--only", default=""); ap.add_argument("--bn", type=int, default=0)
+ap.add_argument("--only", default=""); ap.add_argument("--bn", type=int, default=0); ap.add_argument("--cublas", action="store_true", help="also time torch.matmul (cuBLAS bf16, no epilogue) on the same shape as a library bar")
 a = ap.parse_args()
 F32, BF = torch.float32, torch.bfloat16
 SHAPES = [
@@ -44,5 +44,13 @@ for name, M, N, K, act, od, rd in SHAPES:
     ms = graph_time(fn, a.reps) - t_flush
     total += COUNT[name.split(".")[0]] * ms
     byts = M * K * 2 + N * K * 2 + M * N * (od.itemsize + (rd.itemsize if rd else 0))
-    print(f"{name:9s} {M:7d}x{N:5d}x{K:5d} {ms*1e3:8.1f} us {2*M*N*K/ms/1e9:7.1f} TF/s  {byts/ms/1e6:7.0f} GB/s(algorithmic)", flush=True)
+    extra = ""
+    if a.cublas:
+        wt = w.t().contiguous().t(); ob = torch.empty(M, N, device="cuda", dtype=BF)
+        def fn2():
+            if a.flush: flush.zero_()
+            torch.matmul(x, wt.t() if False else w.t(), out=ob)
+        ms2 = graph_time(fn2, a.reps) - t_flush
+        extra = f"  | cuBLAS bf16 (no epilogue) {ms2*1e3:7.1f} us {2*M*N*K/ms2/1e9:7.1f} TF/s"
+    print(f"{name:9s} {M:7d}x{N:5d}x{K:5d} {ms*1e3:8.1f} us {2*M*N*K/ms/1e9:7.1f} TF/s  {byts/ms/1e6:7.0f} GB/s(algorithmic){extra}", flush=True)
 print(f"sum over the step: {total:.3f} ms (flush {t_flush*1e3:.1f} us subtracted)" )
