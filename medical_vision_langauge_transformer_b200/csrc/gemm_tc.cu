@@ -38,26 +38,29 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;                // 16 KB
 constexpr int B_STAGE_BYTES = (BN_MAX / CG) * BK * 2;     // 16 KB: W rows held per CTA per stage
 constexpr int GEMM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int EPI_PARTS = NUM_EPI_WARPS / 4;              // warps per TMEM lane quarter
 constexpr int TMEM_COLS = 512;
 constexpr int AUX_BYTES = 512;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 // Shared-memory plan of one kernel variant.  The operand ring wants depth (bytes in flight per SM = L2 latency x the
 // 64 B/clk the MMAs consume), the epilogue wants staging buffers; bf16 chunks are 2 KB (32 rows x 64 B), fp32 chunks
-// 4 KB (32 x 128 B), and only the residual variant needs a third buffer (prefetch of chunk k+1 while k-1 still drains).
-template <bool OUT_BF16, bool RES> struct Plan {
-  static constexpr int NBUF = RES ? 3 : 2;
+// 4 KB (32 x 128 B), and the residual variant needs a third buffer (prefetch of chunk k+1 while k-1 still drains).
+// DEEP (residual GEMMs with K >= 1024: fc2 / BERT output.dense): the MMAs of a tile take >= 6000 cycles, so four
+// epilogue warps with two buffers keep up and the ring gets its six stages back.
+template <bool OUT_BF16, bool RES, bool DEEP> struct Plan {
+  static constexpr int EPI_WARPS = DEEP ? 4 : 8;
+  static constexpr int EPI_PARTS = EPI_WARPS / 4;            // warps per TMEM lane quarter
+  static constexpr int NBUF = (RES && !DEEP) ? 3 : 2;
   static constexpr int BUF_BYTES = OUT_BF16 ? 2048 : 4096;
-  static constexpr int EPI_BYTES = NUM_EPI_WARPS * NBUF * BUF_BYTES;
+  static constexpr int EPI_BYTES = EPI_WARPS * NBUF * BUF_BYTES;
   static constexpr int STAGES = (SMEM_LIMIT - 1024 - AUX_BYTES - EPI_BYTES) / (A_STAGE_BYTES + B_STAGE_BYTES) > 6
                                     ? 6 : (SMEM_LIMIT - 1024 - AUX_BYTES - EPI_BYTES) / (A_STAGE_BYTES + B_STAGE_BYTES);
   static constexpr int RING_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
-  static constexpr int NUM_BARS = 2 * STAGES + 4 + NUM_EPI_WARPS * NBUF;
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + EPI_WARPS * NBUF;
   static constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + AUX_BYTES + 1024 /*align slack*/;
   static_assert(NUM_BARS * 8 + 8 <= AUX_BYTES, "barrier block too small");
   static_assert(SMEM_BYTES <= SMEM_LIMIT && STAGES >= 4, "shared memory budget");
+  static_assert(!DEEP || RES, "DEEP is a residual-variant plan");
 };
 
 struct GemmParams {
@@ -109,14 +112,14 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
 }
 
 // ACT: 0 none, 1 erf-GELU, 2 tanh.  OUT_BF16: C is bf16 (else fp32).  RES: C += residual (fp32, via tmap_r; fp32 C only).
-template <int ACT, bool OUT_BF16, bool RES>
+template <int ACT, bool OUT_BF16, bool RES, bool DEEP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, GemmParams p) {
   static_assert(!(RES && OUT_BF16), "residual epilogue is fp32-in/fp32-out");
-  using P = Plan<OUT_BF16, RES>;
+  using P = Plan<OUT_BF16, RES, DEEP>;
   constexpr int STAGES = P::STAGES, EPI_NBUF = P::NBUF, EPI_BUF_BYTES = P::BUF_BYTES, RING_BYTES = P::RING_BYTES;
-  constexpr int EPI_BYTES = P::EPI_BYTES, NUM_BARS = P::NUM_BARS;
+  constexpr int EPI_BYTES = P::EPI_BYTES, NUM_BARS = P::NUM_BARS, NUM_EPI_WARPS = P::EPI_WARPS, EPI_PARTS = P::EPI_PARTS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -224,7 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
     }
-  } else if (warp >= EPI_WARP0) {
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + NUM_EPI_WARPS) {
     // ------------------------------- epilogue (every CTA, its own 128 rows) -----------------
     const int ew = warp - EPI_WARP0;
     const int quarter = warp & 3;   // TMEM lanes [32*quarter, +32) are the only ones this warp may touch
@@ -280,7 +283,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // at most the store of step k-1 is still reading shared memory.  3 buffers (RES): buffer (k+1) % 3, last used by
       // step k-2, is free for the next residual chunk; 2 buffers: buffer k % 2 (step k-2) is free for this step's writes
       if (elect_one()) {
-        bulk_wait_read<1>();
+        // DEEP (2 buffers + residual): the prefetch target (k+1) % 2 was step k-1's buffer -> all stores must have drained
+        if (RES && EPI_NBUF == 2) bulk_wait_read<0>(); else bulk_wait_read<1>();
         if (RES && g + EPI_PARTS < total) {
           int m1, n1;
           chunk_coords(g + EPI_PARTS, m1, n1);
@@ -387,30 +391,33 @@ static int g_num_sms = 0;
 
 typedef void (*GemmKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, GemmParams);
 
-static int smem_bytes(bool out_bf16, bool res) {
-  return out_bf16 ? Plan<true, false>::SMEM_BYTES : res ? Plan<false, true>::SMEM_BYTES : Plan<false, false>::SMEM_BYTES;
+static int smem_bytes(bool out_bf16, bool res, bool deep) {
+  return out_bf16 ? Plan<true, false, false>::SMEM_BYTES
+                  : res ? (deep ? Plan<false, true, true>::SMEM_BYTES : Plan<false, true, false>::SMEM_BYTES)
+                        : Plan<false, false, false>::SMEM_BYTES;
 }
 
-static GemmKernel pick_kernel(int act, bool out_bf16, bool res) {
-#define MVLT_K(A, O, R) gemm_tc_kernel<A, O, R>
+static GemmKernel pick_kernel(int act, bool out_bf16, bool res, bool deep) {
+#define MVLT_K(A, O, R, D) gemm_tc_kernel<A, O, R, D>
   if (out_bf16) {
     switch (act) {
-      case 0: return MVLT_K(0, true, false);
-      case 1: return MVLT_K(1, true, false);
-      default: return MVLT_K(2, true, false);
+      case 0: return MVLT_K(0, true, false, false);
+      case 1: return MVLT_K(1, true, false, false);
+      default: return MVLT_K(2, true, false, false);
     }
   }
   if (res) {
+    if (deep) return MVLT_K(0, false, true, true);  // act == 0 only (checked by the caller)
     switch (act) {
-      case 0: return MVLT_K(0, false, true);
-      case 1: return MVLT_K(1, false, true);
-      default: return MVLT_K(2, false, true);
+      case 0: return MVLT_K(0, false, true, false);
+      case 1: return MVLT_K(1, false, true, false);
+      default: return MVLT_K(2, false, true, false);
     }
   }
   switch (act) {
-    case 0: return MVLT_K(0, false, false);
-    case 1: return MVLT_K(1, false, false);
-    default: return MVLT_K(2, false, false);
+    case 0: return MVLT_K(0, false, false, false);
+    case 1: return MVLT_K(1, false, false, false);
+    default: return MVLT_K(2, false, false, false);
   }
 #undef MVLT_K
 }
@@ -423,11 +430,13 @@ static int gemm_tc_init() {
   if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return MVLT_ERR_DRIVER;
   for (int act = 0; act < 3; ++act)
     for (int o = 0; o < 2; ++o)
-      for (int r = 0; r < 2; ++r) {
-        if (o && r) continue;
-        e = cudaFuncSetAttribute(pick_kernel(act, o != 0, r != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(o != 0, r != 0));
-        if (e != cudaSuccess) return (int)e;
-      }
+      for (int r = 0; r < 2; ++r)
+        for (int d = 0; d < 2; ++d) {
+          if ((o && r) || (d && (!r || act != 0))) continue;
+          e = cudaFuncSetAttribute(pick_kernel(act, o != 0, r != 0, d != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   smem_bytes(o != 0, r != 0, d != 0));
+          if (e != cudaSuccess) return (int)e;
+        }
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -525,7 +534,8 @@ extern "C" int mvlt_gemm_bf16_tc(const void* A, long long lda, const void* W, lo
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = smem_bytes(out_bf16, res);
+  const bool deep = res && act == 0 && K >= 1024;
+  cfg.dynamicSmemBytes = smem_bytes(out_bf16, res, deep);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -534,6 +544,6 @@ extern "C" int mvlt_gemm_bf16_tc(const void* A, long long lda, const void* W, lo
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, pick_kernel(act, out_bf16, res), ta, tb, tc, tr, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, pick_kernel(act, out_bf16, res, deep), ta, tb, tc, tr, p);
   return e == cudaSuccess ? MVLT_OK : (int)e;
 }

@@ -153,7 +153,7 @@ class MVLBert(_PackedMixin, nn.Module):
                 ln2_w=f32(l.output.LayerNorm.weight), ln2_b=f32(l.output.LayerNorm.bias)))
         pk = dict(layers=layers, word=f32(self.word_embeddings.weight))
         if self.pooler is not None:
-            pk["pool_w"], pk["pool_b"] = f32(self.pooler.dense.weight), f32(self.pooler.dense.bias)
+            pk["pool_w"], pk["pool_b"] = wcast(self.pooler.dense.weight), f32(self.pooler.dense.bias)
         return pk
 
     def _typepos(self, pk, n_obj, S):
@@ -202,12 +202,17 @@ class MVLBert(_PackedMixin, nn.Module):
                 taps[f"bert{li}"] = h.clone().view(B, S, -1)
         return h, hb, B, S
 
-    def pool(self, hidden, B, S):
-        """BertPooler (HF modeling_bert.py:456-468): tanh(W h[:,0] + b) as a strided-row fp32 GEMM (B rows only)."""
+    def pool(self, hidden, shadow, B, S):
+        """BertPooler (HF modeling_bert.py:456-468): tanh(W h[:,0] + b) over the B [CLS] rows (row stride S*D).
+        bf16 mode: tcgen05 GEMM on the bf16 shadow rows, pooled returned in bf16 (it only feeds further GEMMs);
+        fp32 mode: CUDA-core GEMM on the fp32 rows."""
         pk = self.packed()
-        pooled = ops.linear(hidden.view(B, S, -1)[:, 0], pk["pool_w"], pk["pool_b"], act=ops.ACT_TANH)
+        if shadow is not None:
+            pooled = ops.linear(shadow.view(B, S, -1)[:, 0], pk["pool_w"], pk["pool_b"], act=ops.ACT_TANH, out_dtype=torch.bfloat16)
+        else:
+            pooled = ops.linear(hidden.view(B, S, -1)[:, 0], pk["pool_w"], pk["pool_b"], act=ops.ACT_TANH)
         if self.taps is not None:
-            self.taps["pooled"] = pooled.clone()
+            self.taps["pooled"] = pooled.float()
         return pooled
 
     def forward(self, text_idx, text_mask, image_feature, image_mask, past_key_values=None, use_cache=False,
@@ -216,9 +221,11 @@ class MVLBert(_PackedMixin, nn.Module):
             raise NotImplementedError("KV-cache decoding (model.py:82-108) is outside the accelerated forward path")
         if text_idx is None:
             raise NotImplementedError("text_idx=None (generation warm-up, model.py:145-147) is outside the accelerated path")
-        hidden, _, B, S = self.encode(text_idx, text_mask, image_feature, image_mask, seq2seq_mask)
+        hidden, shadow, B, S = self.encode(text_idx, text_mask, image_feature, image_mask, seq2seq_mask)
         last = hidden.view(B, S, -1)
-        pooled = self.pool(hidden, B, S) if self.pooler is not None else None
+        pooled = self.pool(hidden, shadow, B, S) if self.pooler is not None else None
+        if pooled is not None and pooled.dtype != torch.float32:
+            pooled = pooled.float()
         if output_text_image_seperate:
             obj_end = image_feature.shape[1] + 1
             text_end = obj_end + text_idx.shape[1] + 1
@@ -301,13 +308,13 @@ class MVLBertForVQA(_PackedMixin, MVLBertPretrainedModel):
 
     def _pack(self):
         lin = self.final_mlp[1]
-        return dict(w=lin.weight.detach().float().contiguous(), b=lin.bias.detach().float().contiguous())
+        return dict(w=lin.weight.detach().to(act_dtype(self.precision)).contiguous(), b=lin.bias.detach().float().contiguous())
 
     def forward(self, image, question, label, image_mask=None):
-        _, hidden, _, B, S = self._trunk(image, question, image_mask)
-        pooled = self.MVLBert.pool(hidden, B, S)
+        _, hidden, shadow, B, S = self._trunk(image, question, image_mask)
+        pooled = self.MVLBert.pool(hidden, shadow, B, S)
         pk = self.packed()
-        logits = ops.linear(pooled, pk["w"], pk["b"])                      # B x result_num: fp32 on the CUDA cores
+        logits = ops.linear(pooled, pk["w"], pk["b"], out_dtype=torch.float32)     # B x result_num
         return ops.softmax_rows(logits), logits
 
 
@@ -329,19 +336,19 @@ class MVLBertForRetrieval(_PackedMixin, MVLBertPretrainedModel):
     def _pack(self):
         t, lin = self.final_mlp[0], self.final_mlp[1]
         f32 = lambda x: x.detach().float().contiguous()
-        return dict(tw=f32(t.dense.weight), tb=f32(t.dense.bias),
+        return dict(tw=t.dense.weight.detach().to(act_dtype(self.precision)).contiguous(), tb=f32(t.dense.bias),
                     lw=f32(t.LayerNorm.weight), lb=f32(t.LayerNorm.bias), w=f32(lin.weight), b=f32(lin.bias))
 
     def head_logits(self, pooled):
         """BertPredictionHeadTransform (HF :471-485) + Linear(768,2) -> fp32 logits [B,2]."""
         pk = self.packed()
-        t = ops.linear(pooled, pk["tw"], pk["tb"], act=ops.ACT_GELU)       # one row per pair: fp32 on the CUDA cores
+        t = ops.linear(pooled, pk["tw"], pk["tb"], act=ops.ACT_GELU, out_dtype=torch.float32)   # one row per pair
         t = ops.layernorm(t, pk["lw"], pk["lb"], self.config.layer_norm_eps, torch.float32)
         return ops.linear_small(t, pk["w"], pk["b"])
 
     def forward(self, image, caption, image_text_label=None, image_mask=None):
-        _, hidden, _, B, S = self._trunk(image, caption, image_mask)
-        logits = self.head_logits(self.MVLBert.pool(hidden, B, S))
+        _, hidden, shadow, B, S = self._trunk(image, caption, image_mask)
+        logits = self.head_logits(self.MVLBert.pool(hidden, shadow, B, S))
         if image_text_label is None:
             return ops.softmax_rows(logits)
         return logits
@@ -398,6 +405,6 @@ class MVLBertForPretraining(_PackedMixin, MVLBertPretrainedModel):
             mlm_loss = acc[0] / acc[1]
         if not cfg.ITM_task:
             return mlm_loss
-        itm_logits = ops.linear_small(self.MVLBert.pool(hidden, B, S), pk["itm_w"], pk["itm_b"])
+        itm_logits = ops.linear_small(self.MVLBert.pool(hidden, shadow, B, S), pk["itm_w"], pk["itm_b"])
         acc = ops.masked_ce(itm_logits, image_text_label.reshape(-1), 2, -100)
         return mlm_loss.mean() + acc[0] / acc[1]

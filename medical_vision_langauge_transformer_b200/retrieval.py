@@ -46,8 +46,8 @@ def score_pairs(model, feats: torch.Tensor, captions: torch.Tensor, pair_batch: 
         p = torch.arange(p0, min(p0 + pair_batch, n_img * n_cap), device=dev)
         img_index = (p // n_cap).to(torch.int32)
         ids = captions.index_select(0, p % n_cap)
-        hidden, _, B, S = bert.encode(ids, None, feats, None, False, img_index=img_index)
-        prob = ops.softmax_rows(model.head_logits(bert.pool(hidden, B, S)))
+        hidden, shadow, B, S = bert.encode(ids, None, feats, None, False, img_index=img_index)
+        prob = ops.softmax_rows(model.head_logits(bert.pool(hidden, shadow, B, S)))
         out[p0:p0 + B] = prob[:, 1]
     return out.view(n_img, n_cap)
 
