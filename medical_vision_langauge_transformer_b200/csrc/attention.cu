@@ -110,6 +110,7 @@ window_attn_warp_kernel(const WinParams p) {
   for (int i = lane; i < 3 * WA_MAT / 8; i += 32) reinterpret_cast<uint4*>(Qs)[i] = make_uint4(0, 0, 0, 0);
   for (int i = lane; i < 64; i += 32) { rowoff[i] = 0; regf[i] = 0.f; }
   __syncwarp();
+  pdl_grid_sync();  // the shared-memory setup above overlapped the previous kernel's tail
 
   const int nW = p.nWh * p.nWw;
   const long long ld_qkv = 3LL * p.C, ld_out = p.C;
@@ -246,6 +247,7 @@ window_attn_warp_kernel(const WinParams p) {
 template <int NPAD>
 __global__ void __launch_bounds__(NPAD * 2, NPAD > 96 ? 2 : 3)
 joint_attn_kernel(const AttnParams p) {
+  pdl_grid_sync();
   constexpr int HD = 64, LDS = HD + 8, NT = NPAD / 8, CPR = HD / 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* Qs = reinterpret_cast<bf16*>(smem_attn);
@@ -359,6 +361,7 @@ joint_attn_kernel(const AttnParams p) {
 template <int HD, bool WINDOW>
 __global__ void __launch_bounds__(256)
 attn_f32_kernel(const AttnParams p, int npad) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int N = p.ntok;
   constexpr int LD = HD + 1;
@@ -465,11 +468,11 @@ extern "C" int mvlt_window_attention(const void* qkv, void* out, int dtype, cons
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ctas = (wp.n_items + WA_WARPS - 1) / WA_WARPS;
     const int gridx = ctas < 3 * sms ? ctas : 3 * sms;  // 3 CTAs (62 KB each) are resident per SM
-    window_attn_warp_kernel<<<gridx, WA_WARPS * 32, WA_WARPS * WA_WARP_BYTES, stream>>>(wp);
+    launch_k(window_attn_warp_kernel, dim3(gridx), dim3(WA_WARPS * 32), WA_WARPS * WA_WARP_BYTES, stream, wp);
   } else if (dtype == MVLT_F32) {
     const int npad = 52;
     const int bytes = (3 * npad * 33 + npad + 49 * (npad + 1)) * 4;
-    attn_f32_kernel<32, true><<<grid, 128, bytes, stream>>>(p, npad);
+    launch_k(attn_f32_kernel<32, true>, dim3(grid), dim3(128), bytes, stream, p, npad);
   } else return MVLT_ERR_INVALID;
   MVLT_LAUNCH_CHECK();
   return MVLT_OK;
@@ -487,15 +490,15 @@ extern "C" int mvlt_joint_attention(const void* qkv, void* out, int dtype, const
   dim3 grid(B, heads);
   if (dtype == MVLT_BF16) {
     if (S <= JOINT_NPAD_S)
-      joint_attn_kernel<JOINT_NPAD_S><<<grid, JOINT_NPAD_S * 2, 3 * JOINT_NPAD_S * 72 * 2 + JOINT_NPAD_S * 4, stream>>>(p);
+      launch_k(joint_attn_kernel<JOINT_NPAD_S>, dim3(grid), dim3(JOINT_NPAD_S * 2), 3 * JOINT_NPAD_S * 72 * 2 + JOINT_NPAD_S * 4, stream, p);
     else if (S <= JOINT_NPAD)
-      joint_attn_kernel<JOINT_NPAD><<<grid, JOINT_NPAD * 2, 3 * JOINT_NPAD * 72 * 2 + JOINT_NPAD * 4, stream>>>(p);
+      launch_k(joint_attn_kernel<JOINT_NPAD>, dim3(grid), dim3(JOINT_NPAD * 2), 3 * JOINT_NPAD * 72 * 2 + JOINT_NPAD * 4, stream, p);
     else return MVLT_ERR_UNSUPPORTED;
   } else if (dtype == MVLT_F32) {
     const int npad = (S + 3) & ~3;
     const int bytes = (3 * npad * 65 + npad + S * (npad + 1)) * 4;
     if (bytes > 200 * 1024) return MVLT_ERR_UNSUPPORTED;
-    attn_f32_kernel<64, false><<<grid, 256, bytes, stream>>>(p, npad);
+    launch_k(attn_f32_kernel<64, false>, dim3(grid), dim3(256), bytes, stream, p, npad);
   } else return MVLT_ERR_INVALID;
   MVLT_LAUNCH_CHECK();
   return MVLT_OK;

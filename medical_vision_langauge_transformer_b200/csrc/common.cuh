@@ -20,9 +20,37 @@
     if (e__ != cudaSuccess) return (int)e__;        \
   } while (0)
 
+// Programmatic dependent launch (PDL).  Every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (unless MVLT_PDL=0) and begins with pdl_grid_sync(): the grid may be
+// scheduled while its predecessor in the stream drains (its CTAs take SMs as they free up, set up barriers / TMEM /
+// descriptors), and only touches global memory after griddepcontrol.wait — which returns once the predecessor has
+// completed and flushed.  The dependents of THIS grid are released right after the wait, so look-ahead is one kernel.
+int mvlt_pdl_enabled(void);  // c_abi.cu
+
 namespace mvlt {
 
 typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                   Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = mvlt_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 

@@ -13,6 +13,7 @@ __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ W, long long ldw,
                  float* __restrict__ C, long long ldc, const float* __restrict__ bias,
                  const float* __restrict__ res, long long ldres, int M, int N, int K, int act) {
+  pdl_grid_sync();
   __shared__ float As[SBK][SBM + 4];
   __shared__ float Bs[SBK][SBN + 4];
   const int tid = threadIdx.x;
@@ -73,7 +74,7 @@ extern "C" int mvlt_gemm_f32_simt(const float* A, long long lda, const float* W,
   if (((uintptr_t)A & 15) || ((uintptr_t)W & 15)) return MVLT_ERR_INVALID;
   dim3 grid((N + mvlt::SBN - 1) / mvlt::SBN, (M + mvlt::SBM - 1) / mvlt::SBM);
   if (grid.y > 65535) return MVLT_ERR_UNSUPPORTED;
-  mvlt::gemm_simt_kernel<<<grid, 256, 0, stream>>>(A, lda, W, ldw, C, ldc, bias, residual, ldres, M, N, K, act);
+  mvlt::launch_k(mvlt::gemm_simt_kernel, dim3(grid), dim3(256), 0, stream, A, lda, W, ldw, C, ldc, bias, residual, ldres, M, N, K, act);
   MVLT_LAUNCH_CHECK();
   return MVLT_OK;
 }

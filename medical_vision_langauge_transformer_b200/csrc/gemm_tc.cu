@@ -168,6 +168,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
+  // global memory is only touched below.
+  pdl_grid_sync();
 
   // Producer and MMA loops run WARP-CONVERGED (all 32 lanes wait on the barriers and track the same loop state) and
   // only the tcgen05 / TMA instructions themselves are predicated on elect.sync: their operands live in uniform
@@ -537,13 +540,15 @@ extern "C" int mvlt_gemm_bf16_tc(const void* A, long long lda, const void* W, lo
   const bool deep = res && act == 0 && K >= 1024;
   cfg.dynamicSmemBytes = smem_bytes(out_bf16, res, deep);
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = mvlt_pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, pick_kernel(act, out_bf16, res, deep), ta, tb, tc, tr, p);
   return e == cudaSuccess ? MVLT_OK : (int)e;
 }

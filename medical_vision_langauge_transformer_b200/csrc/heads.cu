@@ -11,6 +11,7 @@ template <typename TX>
 __global__ void __launch_bounds__(256)
 linear_small_kernel(const TX* __restrict__ x, long long ldx, const float* __restrict__ w, const float* __restrict__ b,
                     float* __restrict__ out, long long rows, int N, int K) {
+  pdl_grid_sync();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -29,6 +30,7 @@ linear_small_kernel(const TX* __restrict__ x, long long ldx, const float* __rest
 
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int N) {
+  pdl_grid_sync();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -48,6 +50,7 @@ softmax_rows_kernel(const float* __restrict__ in, float* __restrict__ out, long 
 __global__ void __launch_bounds__(256)
 masked_ce_rows_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ labels,
                       float* __restrict__ loss_sum, long long rows, int N, long long ignore) {
+  pdl_grid_sync();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -74,8 +77,8 @@ extern "C" int mvlt_linear_small(const void* x, int x_dtype, long long ldx, cons
                                  float* out, long long rows, int N, int K, cudaStream_t stream) {
   if (!x || !w || !out || rows <= 0 || N <= 0 || N > 16 || K % 4 || ldx % 4) return MVLT_ERR_INVALID;
   const unsigned grid = (unsigned)((rows + 7) / 8);
-  if (x_dtype == MVLT_F32) linear_small_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, ldx, w, bias, out, rows, N, K);
-  else if (x_dtype == MVLT_BF16) linear_small_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)x, ldx, w, bias, out, rows, N, K);
+  if (x_dtype == MVLT_F32) launch_k(linear_small_kernel<float>, dim3(grid), dim3(256), 0, stream, (const float*)x, ldx, w, bias, out, rows, N, K);
+  else if (x_dtype == MVLT_BF16) launch_k(linear_small_kernel<bf16>, dim3(grid), dim3(256), 0, stream, (const bf16*)x, ldx, w, bias, out, rows, N, K);
   else return MVLT_ERR_INVALID;
   MVLT_LAUNCH_CHECK();
   return MVLT_OK;
@@ -83,7 +86,7 @@ extern "C" int mvlt_linear_small(const void* x, int x_dtype, long long ldx, cons
 
 extern "C" int mvlt_softmax_rows(const float* in, float* out, long long rows, int N, cudaStream_t stream) {
   if (!in || !out || rows <= 0 || N <= 0) return MVLT_ERR_INVALID;
-  softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(in, out, rows, N);
+  launch_k(softmax_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, stream, in, out, rows, N);
   MVLT_LAUNCH_CHECK();
   return MVLT_OK;
 }
@@ -93,7 +96,7 @@ extern "C" int mvlt_masked_ce_rows(const float* logits, long long ld, const long
   if (!logits || !labels || !loss_sum || rows <= 0 || N <= 0) return MVLT_ERR_INVALID;
   cudaError_t e = cudaMemsetAsync(loss_sum, 0, 2 * sizeof(float), stream);
   if (e != cudaSuccess) return (int)e;
-  masked_ce_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(logits, ld, labels, loss_sum, rows, N, ignore_index);
+  launch_k(masked_ce_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, stream, logits, ld, labels, loss_sum, rows, N, ignore_index);
   MVLT_LAUNCH_CHECK();
   return MVLT_OK;
 }

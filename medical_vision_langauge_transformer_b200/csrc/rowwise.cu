@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const TI* __restrict__ in, long long ld_in, TO* __restrict__ out, long long ld_out,
                       const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, int C, float eps,
                       int gelu, bf16* __restrict__ out_copy, long long ld_copy) {
+  pdl_grid_sync();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const TI* src = in + row * ld_in;
@@ -74,6 +75,7 @@ template <int NCH, typename TO>
 __global__ void __launch_bounds__(256)
 patch_merge_ln_kernel(const float* __restrict__ x, TO* __restrict__ out, const float* __restrict__ gamma,
                       const float* __restrict__ beta, int B, int H, int W, int C, float eps) {
+  pdl_grid_sync();
   const int H2 = H / 2, W2 = W / 2;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= (long long)B * H2 * W2) return;
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(192)
 patch_embed_ln_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
                       float eps) {
+  pdl_grid_sync();
   __shared__ __align__(16) float in_s[3][4][PE_IMG];
   __shared__ float out_s[PE_P][PE_C + 1];
   const int b = blockIdx.x / PE_P, py = blockIdx.x % PE_P;
@@ -153,6 +156,7 @@ joint_embed_kernel(const TF* __restrict__ feat, const int* __restrict__ img_inde
                    const float* __restrict__ word_emb, const float* __restrict__ typepos, TO* __restrict__ out,
                    bf16* __restrict__ out_copy, float* __restrict__ kmask, int B, int n_obj, int L, int D, int cls_id,
                    int sep_id) {
+  pdl_grid_sync();
   const int S = n_obj + 2 + L;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= (long long)B * S) return;
@@ -203,7 +207,7 @@ static int launch_ln(const void* in, long long ld_in, void* out, long long ld_ou
                      long long rows, int C, float eps, int gelu, void* out_copy, long long ld_copy, cudaStream_t st) {
   const unsigned grid = (unsigned)((rows + 7) / 8);
 #define LN_CASE(NCH)                                                                                              \
-  layernorm_rows_kernel<NCH, TI, TO><<<grid, 256, 0, st>>>((const TI*)in, ld_in, (TO*)out, ld_out, gamma, beta, \
+  launch_k(layernorm_rows_kernel<NCH, TI, TO>, dim3(grid), dim3(256), 0, st, (const TI*)in, ld_in, (TO*)out, ld_out, gamma, beta, \
                                                            rows, C, eps, gelu, (bf16*)out_copy, ld_copy)
   if (C <= 128) LN_CASE(1);
   else if (C <= 256) LN_CASE(2);
@@ -241,7 +245,7 @@ extern "C" int mvlt_patch_embed_ln(const float* img, const float* weight, const 
                                    float eps, cudaStream_t stream) {
   if (!img || !weight || !bias || !gamma || !beta || !out || B <= 0) return MVLT_ERR_INVALID;
   if (img_size != PE_IMG || patch != 4 || embed_dim != PE_C) return MVLT_ERR_UNSUPPORTED;  // Swin-S/T/B-224 patch stem
-  patch_embed_ln_kernel<<<B * PE_P, 192, 0, stream>>>(img, weight, bias, gamma, beta, out, eps);
+  launch_k(patch_embed_ln_kernel, dim3(B * PE_P), dim3(192), 0, stream, img, weight, bias, gamma, beta, out, eps);
   MVLT_LAUNCH_CHECK();
   return MVLT_OK;
 }
@@ -254,8 +258,8 @@ extern "C" int mvlt_patch_merge_ln(const float* x, void* out, int out_dtype, con
   const int C4 = 4 * C;
 #define PM_CASE(NCH)                                                                                            \
   do {                                                                                                          \
-    if (out_dtype == MVLT_F32) patch_merge_ln_kernel<NCH, float><<<grid, 256, 0, stream>>>(x, (float*)out, gamma, beta, B, H, W, C, eps); \
-    else patch_merge_ln_kernel<NCH, bf16><<<grid, 256, 0, stream>>>(x, (bf16*)out, gamma, beta, B, H, W, C, eps); \
+    if (out_dtype == MVLT_F32) launch_k(patch_merge_ln_kernel<NCH, float>, dim3(grid), dim3(256), 0, stream, x, (float*)out, gamma, beta, B, H, W, C, eps); \
+    else launch_k(patch_merge_ln_kernel<NCH, bf16>, dim3(grid), dim3(256), 0, stream, x, (bf16*)out, gamma, beta, B, H, W, C, eps); \
   } while (0)
   if (out_dtype != MVLT_F32 && out_dtype != MVLT_BF16) return MVLT_ERR_INVALID;
   if (C4 <= 384) PM_CASE(3);
@@ -278,9 +282,9 @@ extern "C" int mvlt_joint_embed(const void* feat, int feat_dtype, const int* img
   const long long rows = (long long)B * (n_obj + 2 + L);
   const unsigned grid = (unsigned)((rows + 7) / 8);
   if (out_dtype == MVLT_F32)
-    joint_embed_kernel<6, float, float><<<grid, 256, 0, stream>>>((const float*)feat, img_index, ids, text_mask, image_mask, word_emb, typepos, (float*)out, (bf16*)out_bf16_copy, kmask, B, n_obj, L, D, cls_id, sep_id);
+    launch_k(joint_embed_kernel<6, float, float>, dim3(grid), dim3(256), 0, stream, (const float*)feat, img_index, ids, text_mask, image_mask, word_emb, typepos, (float*)out, (bf16*)out_bf16_copy, kmask, B, n_obj, L, D, cls_id, sep_id);
   else if (out_dtype == MVLT_BF16)
-    joint_embed_kernel<6, bf16, bf16><<<grid, 256, 0, stream>>>((const bf16*)feat, img_index, ids, text_mask, image_mask, word_emb, typepos, (bf16*)out, (bf16*)out_bf16_copy, kmask, B, n_obj, L, D, cls_id, sep_id);
+    launch_k(joint_embed_kernel<6, bf16, bf16>, dim3(grid), dim3(256), 0, stream, (const bf16*)feat, img_index, ids, text_mask, image_mask, word_emb, typepos, (bf16*)out, (bf16*)out_bf16_copy, kmask, B, n_obj, L, D, cls_id, sep_id);
   else return MVLT_ERR_INVALID;
   MVLT_LAUNCH_CHECK();
   return MVLT_OK;
