@@ -43,7 +43,16 @@ int mvlt_gemm_bf16_tc(const void* A, long long lda, const void* W, long long ldw
                       const float* bias, const void* residual, long long ldres, int res_dtype, int M, int N, int K,
                       int act, int out_dtype, int block_n, mvlt_stream_t stream);
 
-/* Same contract in fp32 on the CUDA cores (parity mode, 1e-4 vs the reference). */
+/* Fused MLP half of a Swin block, in place on the fp32 residual stream:  x += fc2(GELU(fc1(LayerNorm(x)))).
+ * One tcgen05 kernel per call: LayerNorm in the prologue (fp32 statistics), the [128, 4C] hidden tile stays in shared
+ * memory / TMEM, fp32 accumulate, fp32 residual.  Replaces vfe.py:385 (x + drop_path(mlp(norm2(x))), eval) with
+ * vfe.py:136-139 inside.  x fp32 [M, C] (row stride ldx); gamma/beta/b1/b2 fp32; w1 bf16 [4C, C]; w2 bf16 [C, 4C].
+ * C in {96, 192, 384} (Swin-S stages 0-2; stage 3 uses the unfused kernels), hidden == 4C. */
+int mvlt_swin_mlp_fused(float* x, long long ldx, const float* gamma, const float* beta, float eps, const void* w1,
+                        const float* b1, const void* w2, const float* b2, long long M, int C, int hidden,
+                        mvlt_stream_t stream);
+
+/* Same contract as mvlt_gemm_bf16_tc in fp32 on the CUDA cores (parity mode, 1e-4 vs the reference). */
 int mvlt_gemm_f32_simt(const float* A, long long lda, const float* W, long long ldw, float* C, long long ldc,
                        const float* bias, const float* residual, long long ldres, int M, int N, int K, int act,
                        mvlt_stream_t stream);

@@ -18,6 +18,7 @@ PROTOTYPES = {
     "mvlt_init": [],
     "mvlt_abi_version": [],
     "mvlt_gemm_bf16_tc": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mvlt_swin_mlp_fused": [_vp, _ll, _vp, _vp, _f, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp],
     "mvlt_gemm_f32_simt": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
     "mvlt_layernorm_rows": [_vp, _i, _ll, _vp, _i, _ll, _vp, _vp, _ll, _i, _f, _i, _vp, _ll, _vp],
     "mvlt_patch_embed_ln": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],

@@ -110,6 +110,39 @@ __device__ __forceinline__ float2 gelu_erf_fast2(float2 x) {
   return make_float2(fmaf(-fabsf(x.x), t0, fmaxf(x.x, 0.0f)), fmaf(-fabsf(x.y), t1, fmaxf(x.y, 0.0f)));
 }
 
+// Same fit as gelu_erf_fast, arranged for the fma pipe's issue rate (tools/gemm_trace.py: the GELU epilogues are
+// fma-pipe bound, ~750 cycles per 32x32 chunk per scheduler; a 3-register FFMA or a packed FFMA2 costs 2 / 4 pipe cycles,
+// an FFMA with an immediate operand 1).  GELU(x) = relu(x) - |x| * 2^p(|x|),  p(a) = -1 - q(a) in Horner form with
+// literal coefficients (-1: the 1/2 of Phi folded into the exponent): 5 immediate-form FFMA + MUFU.EX2 + FMNMX + 1 FFMA.
+__device__ __forceinline__ float gelu_erf_imm(float x) {
+  const float a = fabsf(x);
+  float p = fmaf(a, -0.0005292023415677249f, 0.007443261332809925f);
+  p = fmaf(p, a, -0.05264018476009369f);
+  p = fmaf(p, a, -0.45920330286026f);
+  p = fmaf(p, a, -1.1511013507843018f);
+  p = fmaf(p, a, -1.0f);
+  float t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(p));
+  return fmaf(-a, t, fmaxf(x, 0.0f));
+}
+
+// The same fit once more, for an ISSUE-bound consumer (the GEMM epilogues: ~1 instruction per scheduler cycle while
+// they run): 12 issued instructions per PAIR.  With n = -|x| (sign bit OR, alu pipe) the exponent polynomial is
+// p(n) = -1 + c1 n - c2 n^2 + c3 n^3 - c4 n^4 + c5 n^5 in packed Horner form (5 FFMA2), then 2 MUFU.EX2, 2 FMNMX for
+// relu(x) and one packed FFMA2 for relu(x) + n * 2^p.
+__device__ __forceinline__ float2 gelu_erf_pk2(float2 x) {
+  const float2 n = make_float2(__uint_as_float(__float_as_uint(x.x) | 0x80000000u), __uint_as_float(__float_as_uint(x.y) | 0x80000000u));
+  float2 p = fma2(n, make_float2(0.0005292023415677249f, 0.0005292023415677249f), make_float2(0.007443261332809925f, 0.007443261332809925f));
+  p = fma2(p, n, make_float2(0.05264018476009369f, 0.05264018476009369f));
+  p = fma2(p, n, make_float2(-0.45920330286026f, -0.45920330286026f));
+  p = fma2(p, n, make_float2(1.1511013507843018f, 1.1511013507843018f));
+  p = fma2(p, n, make_float2(-1.0f, -1.0f));
+  float t0, t1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(p.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(p.y));
+  return fma2(n, make_float2(t0, t1), make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -27,6 +27,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tmap.cuh"
 
 namespace mvlt {
 
@@ -36,7 +37,6 @@ constexpr int BK = 64;   // 64 bf16 = 128 B = one swizzle span
 constexpr int BN_MAX = 256;
 constexpr int A_STAGE_BYTES = BM * BK * 2;                // 16 KB
 constexpr int B_STAGE_BYTES = (BN_MAX / CG) * BK * 2;     // 16 KB: W rows held per CTA per stage
-constexpr int GEMM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int TMEM_COLS = 512;
 constexpr int AUX_BYTES = 512;
@@ -48,18 +48,25 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 // DEEP (residual GEMMs with K >= 1024: fc2 / BERT output.dense): the MMAs of a tile take >= 6000 cycles, so four
 // epilogue warps with two buffers keep up and the ring gets its six stages back.
 template <bool OUT_BF16, bool RES, bool DEEP> struct Plan {
-  static constexpr int EPI_WARPS = DEEP ? 4 : 8;
+  // bf16 outputs (qkv, fc1/FFN-in + GELU): the per-chunk chain tcgen05.ld -> bias -> GELU -> pack -> st.shared -> fence ->
+  // TMA store is latency-bound with two warps per scheduler (measured 1900 cycles per 32x32 chunk for ~300 issued
+  // instructions, tools/gemm_trace.py) and those call sites are epilogue-bound: 16 warps = four per scheduler.
+  static constexpr int EPI_WARPS = DEEP ? 4 : (OUT_BF16 ? 16 : 8);
+  static constexpr int THREADS = (4 + EPI_WARPS) * 32;       // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare
   static constexpr int EPI_PARTS = EPI_WARPS / 4;            // warps per TMEM lane quarter
-  static constexpr int NBUF = (RES && !DEEP) ? 3 : 2;
+  // staging buffers per warp: the residual variant prefetches chunk k+1 while k-1 still drains (3; DEEP: 2); with four
+  // warps per scheduler a single buffer is enough — its previous store drains during the next chunk's tcgen05.ld + math
+  static constexpr int NBUF = RES ? (DEEP ? 2 : 3) : (OUT_BF16 ? 1 : 2);
   static constexpr int BUF_BYTES = OUT_BF16 ? 2048 : 4096;
-  static constexpr int EPI_BYTES = EPI_WARPS * NBUF * BUF_BYTES;
+  static constexpr int STAGING_BYTES = EPI_WARPS * NBUF * BUF_BYTES;
+  static constexpr int EPI_BYTES = STAGING_BYTES + EPI_WARPS * 128;   // + one 32-float bias slot per warp
   static constexpr int STAGES = (SMEM_LIMIT - 1024 - AUX_BYTES - EPI_BYTES) / (A_STAGE_BYTES + B_STAGE_BYTES) > 6
                                     ? 6 : (SMEM_LIMIT - 1024 - AUX_BYTES - EPI_BYTES) / (A_STAGE_BYTES + B_STAGE_BYTES);
   static constexpr int RING_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
   static constexpr int NUM_BARS = 2 * STAGES + 4 + EPI_WARPS * NBUF;
   static constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + AUX_BYTES + 1024 /*align slack*/;
   static_assert(NUM_BARS * 8 + 8 <= AUX_BYTES, "barrier block too small");
-  static_assert(SMEM_BYTES <= SMEM_LIMIT && STAGES >= 4, "shared memory budget");
+  static_assert(SMEM_BYTES <= SMEM_LIMIT && STAGES >= 4 && THREADS <= 1024, "shared memory budget");
   static_assert(!DEEP || RES, "DEEP is a residual-variant plan");
 };
 
@@ -68,7 +75,10 @@ struct GemmParams {
   int M, N, K;
   int block_n;
   int tiles_m, tiles_n;
+  unsigned long long* trace;  // debug: clock64 stamps of CTA 0 (tools/gemm_trace.py); nullptr in production
 };
+static unsigned long long* g_gemm_trace = nullptr;
+#define GEMM_STAMP(idx) do { if (p.trace != nullptr && blockIdx.x == 0 && lane == 0) p.trace[(idx)] = (unsigned long long)clock64(); } while (0)
 
 // ---- cta_group::2 PTX ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst, uint32_t ncols) {
@@ -113,7 +123,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
 
 // ACT: 0 none, 1 erf-GELU, 2 tanh.  OUT_BF16: C is bf16 (else fp32).  RES: C += residual (fp32, via tmap_r; fp32 C only).
 template <int ACT, bool OUT_BF16, bool RES, bool DEEP>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__((Plan<OUT_BF16, RES, DEEP>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, GemmParams p) {
   static_assert(!(RES && OUT_BF16), "residual epilogue is fp32-in/fp32-out");
@@ -136,6 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (warp == 0) GEMM_STAMP(0);
   const uint32_t rank = cluster_ctarank();
   const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
   const int num_tiles = p.tiles_m * p.tiles_n;
@@ -168,9 +179,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (warp == 0) GEMM_STAMP(1);
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
   // global memory is only touched below.
   pdl_grid_sync();
+  if (warp == 0) GEMM_STAMP(2);
 
   // Producer and MMA loops run WARP-CONVERGED (all 32 lanes wait on the barriers and track the same loop state) and
   // only the tcgen05 / TMA instructions themselves are predicated on elect.sync: their operands live in uniform
@@ -207,11 +220,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t acc = it & 1, acc_ph = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
         tc_fence_after();
+        if (it < 16) GEMM_STAMP(16 + 4 * it);
         const uint32_t tmem_d = tmem_base + acc * BN_MAX;
         for (int kb = 0; kb < num_kb; ++kb, ++kc) {
           const uint32_t s = kc % STAGES, ph = (kc / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (kb == 0 && it < 16) GEMM_STAMP(16 + 4 * it + 1);
           const uint32_t lo_a = lo_a0 + s * (A_STAGE_BYTES >> 4);
           const uint32_t lo_b = lo_b0 + s * (B_STAGE_BYTES >> 4);
           const int ksteps = min(BK, p.K - kb * BK) / 16;  // K % 16 == 0 is checked on the host
@@ -227,6 +242,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (kb == num_kb - 1) umma_commit_cg2(&tmem_full[acc]);  // accumulator complete (both CTAs' epilogues)
           }
           __syncwarp();
+          if (kb == num_kb - 1 && it < 16) GEMM_STAMP(16 + 4 * it + 2);
         }
       }
     }
@@ -237,8 +253,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int part = ew >> 2;       // this warp takes the chunks g == part (mod EPI_PARTS) of the CTA's chunk sequence
     const int chunks = p.block_n >> 5;
     const int my_tiles = (num_tiles - group + num_groups - 1) / num_groups;
-    const int total = my_tiles * chunks;
     uint8_t* bufs = smem_epi + ew * (EPI_NBUF * EPI_BUF_BYTES);
+    float* sbias = reinterpret_cast<float*>(smem_epi + P::STAGING_BYTES) + ew * 32;  // this warp's bias slot (32 columns)
     uint64_t* rbar = res_full + ew * EPI_NBUF;
     // byte offset of 16 B slot j of this thread's row inside a staging buffer, TMA swizzle applied:
     //   fp32: 128 B rows, SWIZZLE_128B: slot j -> j ^ (row & 7);   bf16: 64 B rows, SWIZZLE_64B: slot j -> j ^ ((row >> 1) & 3)
@@ -246,17 +262,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t swz = OUT_BF16 ? ((lane >> 1) & 3u) : (lane & 7u);
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
 
-    // (tile row0, column0) of sequence element g
-    auto chunk_coords = [&](int g, int& m0, int& n0) {
-      const int ti = g / chunks, c = g - ti * chunks;
-      const int tile = group + ti * num_groups;
-      m0 = (tile / p.tiles_n) * (BM * CG) + rank * BM + quarter * 32;
-      n0 = (tile % p.tiles_n) * p.block_n + c * 32;
+    // Position of this warp in its chunk sequence g = part, part + EPI_PARTS, ... (g = ti * chunks + c), advanced
+    // incrementally: the divisions by runtime tile counts happen once per tile, not three times per chunk (they were a
+    // third of the instructions the issue-bound epilogue executed, ncu source page of v8).
+    struct Pos { int ti, c, m0, n0t; };  // tile iteration, chunk in tile, row0 of this warp's 32 rows, column0 of the tile
+    auto tile_origin = [&](Pos& s) {
+      const int tile = group + s.ti * num_groups;
+      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      s.m0 = tm * (BM * CG) + rank * BM + quarter * 32;
+      s.n0t = tn * p.block_n;
     };
+    auto normalize = [&](Pos& s) {
+      if (s.c >= chunks) {
+        do { s.c -= chunks; ++s.ti; } while (s.c >= chunks);
+        if (s.ti < my_tiles) tile_origin(s);
+      }
+    };
+    // bias of a chunk, one column per lane (0 beyond N: no ragged-edge path in the chunk loop).  Fetched one step ahead
+    // and parked in shared memory: the chunk loop never waits on an L2 round trip for it.
+    auto bias_fetch = [&](int n0) -> float {
+      const int n = n0 + lane;
+      return (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f;
+    };
+    Pos cur;
+    cur.ti = 0; cur.c = part; cur.m0 = 0; cur.n0t = 0;
+    tile_origin(cur);
+    normalize(cur);
+    float bias_next = cur.ti < my_tiles ? bias_fetch(cur.n0t + cur.c * 32) : 0.f;
     if (RES) {
-      if (part < total) {
-        int m0, n0;
-        chunk_coords(part, m0, n0);
+      if (cur.ti < my_tiles) {
+        const int m0 = cur.m0, n0 = cur.n0t + cur.c * 32;
         if (n0 < p.N && m0 < p.M && elect_one()) {
           mbar_arrive_expect_tx(&rbar[0], 32 * 32 * 4);
           tma_load_2d(bufs, &tmap_r, &rbar[0], n0, m0);
@@ -269,28 +304,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tmem_empty[ti & 1], 0);
+      if (ew == 0 && ti < 16) GEMM_STAMP(128 + 4 * ti + 1);
     };
     auto acquire_tile = [&](int ti) {
       mbar_wait(&tmem_full[ti & 1], (ti >> 1) & 1);
       tc_fence_after();
+      if (ew == 0 && ti < 16) GEMM_STAMP(128 + 4 * ti);
     };
     int k = 0;
     uint32_t res_parity = 0;  // bit b: parity of the next residual load to land in staging buffer b
-    for (int g = part; g < total; g += EPI_PARTS, ++k) {
-      const int ti = g / chunks, c = g - ti * chunks;
+    for (; cur.ti < my_tiles; ++k) {
+      const int ti = cur.ti, c = cur.c;
       const int buf = k % EPI_NBUF;
       uint8_t* sb = bufs + buf * EPI_BUF_BYTES;
-      int m0, n0;
-      chunk_coords(g, m0, n0);
+      const int m0 = cur.m0, n0 = cur.n0t + c * 32;
       const bool live = n0 < p.N && m0 < p.M;  // warp-uniform: the chunk holds at least one real element
+      Pos nxt = cur;
+      nxt.c += EPI_PARTS;
+      normalize(nxt);
+      const bool has_next = nxt.ti < my_tiles;
+      const int m1 = nxt.m0, n1 = nxt.n0t + nxt.c * 32;
+      const bool tr_on = ew == 0 && k < 24;
+      if (tr_on) GEMM_STAMP(256 + 8 * k);
+      sbias[lane] = bias_next;  // visible to the whole warp after the __syncwarp below
+      if (has_next) bias_next = bias_fetch(n1);
       // at most the store of step k-1 is still reading shared memory.  3 buffers (RES): buffer (k+1) % 3, last used by
       // step k-2, is free for the next residual chunk; 2 buffers: buffer k % 2 (step k-2) is free for this step's writes
-      if (elect_one()) {
-        // DEEP (2 buffers + residual): the prefetch target (k+1) % 2 was step k-1's buffer -> all stores must have drained
-        if (RES && EPI_NBUF == 2) bulk_wait_read<0>(); else bulk_wait_read<1>();
-        if (RES && g + EPI_PARTS < total) {
-          int m1, n1;
-          chunk_coords(g + EPI_PARTS, m1, n1);
+      if (RES && elect_one()) {
+        // at most the store of step k-1 is still reading shared memory: buffer (k+1) % 3, last used by step k-2, is free
+        // for the next residual chunk.  DEEP (2 buffers): the prefetch target was step k-1's buffer -> drain everything
+        if (EPI_NBUF == 2) bulk_wait_read<0>(); else bulk_wait_read<1>();
+        if (has_next) {
           if (n1 < p.N && m1 < p.M) {
             const int nb = (k + 1) % EPI_NBUF;
             mbar_arrive_expect_tx(&rbar[nb], 32 * 32 * 4);
@@ -299,11 +343,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
       __syncwarp();
+      if (tr_on) GEMM_STAMP(256 + 8 * k + 1);
       while (cur_ti < ti) {  // also passes through tiles in which this warp owns no chunk (block_n = 32)
         if (cur_ti >= 0) release_tile(cur_ti);
         ++cur_ti;
         acquire_tile(cur_ti);
       }
+      if (tr_on) GEMM_STAMP(256 + 8 * k + 2);
       if (live) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_lane + (uint32_t)((ti & 1) * BN_MAX + c * 32), r);
@@ -312,32 +358,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           res_parity ^= 1u << buf;
         }
         tmem_ld_wait();
+        if (tr_on) GEMM_STAMP(256 + 8 * k + 3);
         float2 v[16];  // this thread's row: 32 consecutive columns as 16 packed pairs
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
         if (p.bias != nullptr) {
-          if (n0 + 32 <= p.N) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
-              v[2 * j] = add2(v[2 * j], make_float2(b.x, b.y));
-              v[2 * j + 1] = add2(v[2 * j + 1], make_float2(b.z, b.w));
-            }
-          } else {  // ragged N edge
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int n = n0 + 2 * i;
-              v[i].x += n < p.N ? __ldg(p.bias + n) : 0.f;
-              v[i].y += n + 1 < p.N ? __ldg(p.bias + n + 1) : 0.f;
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = *(reinterpret_cast<const float4*>(sbias) + j);  // broadcast read
+            v[2 * j] = add2(v[2 * j], make_float2(b.x, b.y));
+            v[2 * j + 1] = add2(v[2 * j + 1], make_float2(b.z, b.w));
           }
         }
         if (ACT == 1) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = gelu_erf_fast2(v[i]);
+          for (int i = 0; i < 16; ++i) v[i] = gelu_erf_pk2(v[i]);
         } else if (ACT == 2) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = make_float2(tanhf(v[i].x), tanhf(v[i].y));
+        }
+        if (tr_on) GEMM_STAMP(256 + 8 * k + 4);
+        if (!RES) {  // buffer k % NBUF was last read by the store of step k - NBUF
+          if (elect_one()) bulk_wait_read<EPI_NBUF - 1>();
+          __syncwarp();
         }
         if (OUT_BF16) {
           // 8 bf16 (4 pairs) per 16 B slot
@@ -347,26 +390,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 make_uint4(pack_bf16x2(v[4 * j].x, v[4 * j].y), pack_bf16x2(v[4 * j + 1].x, v[4 * j + 1].y),
                            pack_bf16x2(v[4 * j + 2].x, v[4 * j + 2].y), pack_bf16x2(v[4 * j + 3].x, v[4 * j + 3].y));
         } else {
+          float4 t[8];
+          if (RES) {  // all eight loads before the first store: the in-place slots alias as far as the compiler can tell
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = *reinterpret_cast<const float4*>(sb + row_base + (((uint32_t)j ^ swz) << 4));
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float4* slot = reinterpret_cast<float4*>(sb + row_base + (((uint32_t)j ^ swz) << 4));
             float2 a = v[2 * j], b = v[2 * j + 1];
             if (RES) {
-              const float4 t = *slot;
-              a = add2(a, make_float2(t.x, t.y));
-              b = add2(b, make_float2(t.z, t.w));
+              a = add2(a, make_float2(t[j].x, t[j].y));
+              b = add2(b, make_float2(t[j].z, t[j].w));
             }
-            *slot = make_float4(a.x, a.y, b.x, b.y);
+            *reinterpret_cast<float4*>(sb + row_base + (((uint32_t)j ^ swz) << 4)) = make_float4(a.x, a.y, b.x, b.y);
           }
         }
+        if (tr_on) GEMM_STAMP(256 + 8 * k + 5);
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA unit
       }
       __syncwarp();
+      if (tr_on) GEMM_STAMP(256 + 8 * k + 6);
       if (elect_one()) {
         if (live) tma_store_2d(&tmap_c, sb, n0, m0);
         bulk_commit();  // one group per step (empty when the chunk lies beyond N) keeps the wait_group arithmetic uniform
       }
       __syncwarp();
+      if (tr_on) GEMM_STAMP(256 + 8 * k + 7);
+      cur = nxt;
     }
     while (cur_ti < my_tiles - 1) {
       if (cur_ti >= 0) release_tile(cur_ti);
@@ -376,10 +426,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (cur_ti >= 0) release_tile(cur_ti);
     if (elect_one()) bulk_wait_all();  // all of this warp's stores have left shared memory and are globally performed
     __syncwarp();
+    if (ew == 0) GEMM_STAMP(3);
   }
 
   tc_fence_before();
   cluster_sync_all();
+  if (warp == 0) GEMM_STAMP(4);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_cg2(tmem_base, TMEM_COLS);
@@ -447,8 +499,8 @@ static int gemm_tc_init() {
   return MVLT_OK;
 }
 
-// 2-D row-major tensor map: dims {cols, rows}, row stride ld_elems, box {box_cols, box_rows}
-static int make_tmap(CUtensorMap* map, CUtensorMapDataType dt, int elt_bytes, const void* ptr, long long rows, long long cols,
+// 2-D row-major tensor map: dims {cols, rows}, row stride ld_elems, box {box_cols, box_rows}  (declared in tmap.cuh)
+int make_tmap(CUtensorMap* map, CUtensorMapDataType dt, int elt_bytes, const void* ptr, long long rows, long long cols,
                      long long ld_elems, int box_cols, int box_rows, CUtensorMapSwizzle swz, CUtensorMapL2promotion promo) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld_elems * elt_bytes};
@@ -489,6 +541,12 @@ static int pick_block_n(int M, int N, int K, int groups) {
 using namespace mvlt;
 
 extern "C" int mvlt_gemm_tc_init(void) { return gemm_tc_init(); }
+
+// debug hook (not part of include/mvlt_b200.h): device buffer of >= 256 u64 stamped by CTA 0 of every later launch
+extern "C" int mvlt_debug_gemm_trace(void* dev_buf) {
+  g_gemm_trace = reinterpret_cast<unsigned long long*>(dev_buf);
+  return MVLT_OK;
+}
 
 extern "C" int mvlt_gemm_bf16_tc(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc,
                                  const float* bias, const void* residual, long long ldres, int res_dtype, int M, int N,
@@ -531,13 +589,14 @@ extern "C" int mvlt_gemm_bf16_tc(const void* A, long long lda, const void* W, lo
   p.bias = bias; p.M = M; p.N = N; p.K = K; p.block_n = block_n;
   p.tiles_m = (M + BM * CG - 1) / (BM * CG);
   p.tiles_n = (N + block_n - 1) / block_n;
+  p.trace = g_gemm_trace;
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = CG * (tiles < groups ? tiles : groups);
 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GEMM_THREADS);
   const bool deep = res && act == 0 && K >= 1024;
+  cfg.blockDim = dim3(out_bf16 ? Plan<true, false, false>::THREADS : (deep ? Plan<false, true, true>::THREADS : Plan<false, false, false>::THREADS));
   cfg.dynamicSmemBytes = smem_bytes(out_bf16, res, deep);
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];

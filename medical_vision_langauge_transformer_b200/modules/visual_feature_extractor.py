@@ -235,6 +235,10 @@ class SwinTransformer(nn.Module):
         adt = act_dtype(self.precision)
         x = x.contiguous().float()
         X = ops.patch_embed_ln(x, pk["pe_w"], pk["pe_b"], pe.norm.weight, pe.norm.bias, pe.norm.eps)
+        # MVLT_FUSED_MLP=1 (experimental, bf16 mode): LN2 + fc1 + GELU + fc2 + residual as ONE kernel (csrc/swin_mlp.cu) for the
+        # stage widths whose fc2 accumulator fits TMEM.  Parity-green but shared-memory-bandwidth bound at N=64 MMAs (84 us vs
+        # 51 us for the unfused chain at stage 2), so the unfused kernels stay the default.
+        fused_mlp = self.precision == "bf16" and os.environ.get("MVLT_FUSED_MLP", "0") == "1"
         taps = self.taps
         if taps is not None:
             taps["patch_embed"] = X.clone().view(B, -1, X.shape[-1])
@@ -251,9 +255,12 @@ class SwinTransformer(nn.Module):
                 o = ops.window_attention(qkv, w["relbias"], B, H, W, C, blk.num_heads, blk.window_size, blk.shift_size,
                                          blk.attn.scale)
                 ops.linear(o, w["proj_w"], w["proj_b"], residual=X, out=X)
-                a = ops.layernorm(X, w["n2w"], w["n2b"], blk.norm2.eps, adt)
-                h = ops.linear(a, w["fc1_w"], w["fc1_b"], act=ops.ACT_GELU)
-                ops.linear(h, w["fc2_w"], w["fc2_b"], residual=X, out=X)
+                if fused_mlp and C in ops.FUSED_MLP_WIDTHS and w["fc1_w"].shape[0] == 4 * C:
+                    ops.swin_mlp(X, w["n2w"], w["n2b"], blk.norm2.eps, w["fc1_w"], w["fc1_b"], w["fc2_w"], w["fc2_b"])
+                else:
+                    a = ops.layernorm(X, w["n2w"], w["n2b"], blk.norm2.eps, adt)
+                    h = ops.linear(a, w["fc1_w"], w["fc1_b"], act=ops.ACT_GELU)
+                    ops.linear(h, w["fc2_w"], w["fc2_b"], residual=X, out=X)
                 if taps is not None and i < 2:
                     taps[f"s{s}b{i}"] = X.clone().view(B, H * W, C)
             if layer.downsample is not None:

@@ -70,6 +70,25 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out
 
 
+FUSED_MLP_WIDTHS = (96, 192, 384)
+
+
+def swin_mlp(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, w1: torch.Tensor, b1: torch.Tensor,
+             w2: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
+    """x += fc2(gelu(fc1(layernorm(x)))) in place, one kernel (fp32 x, bf16 weights, C in FUSED_MLP_WIDTHS)."""
+    lib = _lib.ensure_init()
+    M, C, ldx = _rows2d(x)
+    hidden = w1.shape[0]
+    assert x.dtype == torch.float32 and w1.dtype == w2.dtype == torch.bfloat16
+    assert w1.shape == (hidden, C) and w2.shape == (C, hidden) and w1.is_contiguous() and w2.is_contiguous()
+    for t, n in ((gamma, C), (beta, C), (b1, hidden), (b2, C)):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n
+    rc = lib.mvlt_swin_mlp_fused(x.data_ptr(), ldx, gamma.data_ptr(), beta.data_ptr(), float(eps), w1.data_ptr(),
+                                 b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), M, C, hidden, _stream())
+    _lib.check(rc, f"mvlt_swin_mlp_fused(M={M},C={C})")
+    return x
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out_dtype: torch.dtype,
               gelu: bool = False, out: Optional[torch.Tensor] = None, bf16_copy: bool = False):
     """LayerNorm rows.  bf16_copy=True additionally returns the rows rounded to bf16 (-> (out, copy))."""

@@ -123,6 +123,31 @@ def test_gemm_tc_inplace_residual_and_strided_a(cuda):
     assert relerr(out, ref) < 2e-3
 
 
+@pytest.mark.parametrize("C,M", [(96, 6272), (96, 300), (96, 1), (192, 1568), (192, 129), (384, 392), (384, 12544),
+                                 (384, 127)])
+def test_swin_mlp_fused(cuda, C, M):
+    """x += fc2(gelu(fc1(LN(x)))) as one kernel (vfe.py:385 + :136-139) against (a) a torch restatement that rounds the
+    LN output and the hidden activation to bf16 where the kernel does and (b) the unfused kernel chain, in place, at
+    full tiles, ragged last tiles and a single row."""
+    from medical_vision_langauge_transformer_b200 import ops
+    x = rnd(M, C, seed=C + M) * 2 + 0.3
+    g, b = 1 + rnd(C, seed=1, scale=0.1), rnd(C, seed=2, scale=0.1)
+    w1, b1 = rnd(4 * C, C, seed=3, scale=C ** -0.5).bfloat16(), rnd(4 * C, seed=4, scale=0.2)
+    w2, b2 = rnd(C, 4 * C, seed=5, scale=(4 * C) ** -0.5).bfloat16(), rnd(C, seed=6, scale=0.2)
+    a_ref = F.layer_norm(x, (C,), g, b, 1e-5).bfloat16().float()
+    h_ref = F.gelu(a_ref @ w1.float().t() + b1).bfloat16().float()
+    ref = x + h_ref @ w2.float().t() + b2
+    a = ops.layernorm(x, g, b, 1e-5, torch.bfloat16)
+    h = ops.linear(a, w1, b1, act=ops.ACT_GELU)
+    chain = ops.linear(h, w2, b2, residual=x, out_dtype=torch.float32)
+    pad = torch.full((M + 3, C), 7.0, device="cuda")
+    pad[:M] = x
+    out = ops.swin_mlp(pad[:M], g, b, 1e-5, w1, b1, w2, b2)
+    assert relerr(out, ref) < 3e-3, (C, M)
+    assert relerr(out, chain) < 3e-3, (C, M)
+    assert torch.all(pad[M:] == 7.0)          # rows past M untouched
+
+
 @pytest.mark.parametrize("M,N,K", [(130, 100, 48), (262, 2304, 768), (1000, 96, 384), (64, 224, 768)])
 def test_gemm_simt(cuda, M, N, K):
     from medical_vision_langauge_transformer_b200 import ops
