@@ -76,8 +76,11 @@ int mvlt_patch_merge_ln(const float* x, void* out, int out_dtype, const float* g
                         int W, int C, float eps, mvlt_stream_t stream);
 
 /* Shifted-window attention with tokens in natural order: qkv [B*H*W, 3C] -> out [B*H*W, C]; the roll / partition /
- * reverse of vfe.py:144-173,:361,:378 are folded into the row index map.  relbias fp32 [heads,64,64] = the gathered
- * relative_position_bias (vfe.py:236-238), zero padded.  shift > 0 adds the -100 region mask of vfe.py:318-344. */
+ * reverse of vfe.py:144-173,:361,:378 are folded into the row index map.  shift > 0 adds the -100 region mask of
+ * vfe.py:318-344.  relbias, dtype fp32: [heads,64,64] = the gathered relative_position_bias (vfe.py:236-238), zero
+ * padded.  relbias, dtype bf16: the same bias with the shift mask added and 1/scale folded in, repacked in
+ * mma.m16n8 C-fragment order as fp32 [n_cls, heads, 4, 7, 32, 4] (n_cls = 4 window classes when shift > 0, else 1;
+ * key columns 49..55 = -1e30), 16-byte aligned — built once per block by the host (ops.window_bias_fragments). */
 int mvlt_window_attention(const void* qkv, void* out, int dtype, const float* relbias, int B, int H, int W, int C,
                           int heads, int window, int shift, float scale, mvlt_stream_t stream);
 

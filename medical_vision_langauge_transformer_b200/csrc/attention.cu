@@ -78,25 +78,32 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr float NEG_BIG = -1.0e30f;  // "minus infinity" that stays finite through (x - max) and scale multiplies
 
 // ---- Swin window attention, bf16: ONE WARP per (image, window, head) ------------------------------------------------
-// The 49x32 q, k, v slices of the item are cp.async'ed into this warp's private 15 KB of shared memory (rows found
-// through the roll/partition index map, computed once per item), K fragments are held in registers across the four
-// 16-row query tiles, the score accumulators are INITIALISED with (rel-pos bias + shift mask) / scale so that
-// exp2(scale*log2e * acc - max) needs one FFMA + one MUFU per score, and P.V runs from the S fragments in registers.
-// No __syncthreads anywhere: the four warps of a CTA are independent pipelines (loads of one overlap math of another).
-constexpr int WA_LDS = 40;                                   // padded row (bf16 elements): conflict-free ldmatrix
-constexpr int WA_MAT = 64 * WA_LDS;                          // elements per staged matrix
-constexpr int WA_WARP_BYTES = 3 * WA_MAT * 2 + 64 * 4 + 64 * 4;  // Q,K,V + row index table + region ids
-constexpr int WA_WARPS = 4;
+// The 49x32 q, k, v slices of the item are cp.async'ed into this warp's private 12 KB of shared memory (64-byte rows,
+// 16-byte chunks XOR-swizzled by (row >> 1) & 3: conflict-free ldmatrix without padding -> 16 warps per SM), rows found
+// through the roll/partition index map computed once per item.  K fragments stay in registers across the four 16-row
+// query tiles.  The score accumulators are INITIALISED from a host-built table that already holds
+// (rel-pos bias + shift mask) / scale in the mma C-fragment layout, one float4 per (class, head, m-tile, n-tile, lane),
+// with -1e30 in the columns of the non-existent keys 49..55: no bias gather, no mask logic, no scaling in the kernel,
+// and exp2(scale*log2e * acc - max) is one FFMA + one MUFU per score.  P.V runs from the S fragments in registers.
+// No __syncthreads anywhere: the warps of a CTA are independent pipelines (loads of one overlap math of another).
+constexpr int WA_ROW = 32;                                   // bf16 elements per staged row (64 B)
+constexpr int WA_MAT = 64 * WA_ROW;                          // elements per staged matrix (4 KB)
+constexpr int WA_WARP_BYTES = 3 * WA_MAT * 2 + 64 * 4;       // Q, K, V + row index table
+constexpr int WA_WARPS = 8;
+constexpr int WA_CTAS_PER_SM = 2;
+
+// element offset of 16-byte chunk `chunk` (0..3) of row `row` in a staged matrix
+__device__ __forceinline__ int wa_off(int row, int chunk) { return row * WA_ROW + ((chunk ^ ((row >> 1) & 3)) << 3); }
 
 struct WinParams {
   const bf16* qkv;
   bf16* out;
-  const float* relbias;  // [heads, 64, 64] fp32, zero padded
+  const float4* bias_frag;  // [n_cls, heads, 4 m-tiles, 7 n-tiles, 32 lanes] float4 (see ops.window_bias_fragments)
   int H, W, C, heads, shift, n_items, nWh, nWw;
   float scale;
 };
 
-__global__ void __launch_bounds__(WA_WARPS * 32)
+__global__ void __launch_bounds__(WA_WARPS * 32, WA_CTAS_PER_SM)
 window_attn_warp_kernel(const WinParams p) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -105,20 +112,20 @@ window_attn_warp_kernel(const WinParams p) {
   bf16* Ks = Qs + WA_MAT;
   bf16* Vs = Ks + WA_MAT;
   int* rowoff = reinterpret_cast<int*>(Vs + WA_MAT);   // token i of this window -> row of the [B*H*W, .] matrices
-  float* regf = reinterpret_cast<float*>(rowoff + 64);  // region id of token i in the shifted image (vfe.py:321-339)
   // padding rows (tokens 49..63) are zero for the whole kernel: loads only ever touch rows 0..48
   for (int i = lane; i < 3 * WA_MAT / 8; i += 32) reinterpret_cast<uint4*>(Qs)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = lane; i < 64; i += 32) { rowoff[i] = 0; regf[i] = 0.f; }
+  for (int i = lane; i < 64; i += 32) rowoff[i] = 0;
   __syncwarp();
   pdl_grid_sync();  // the shared-memory setup above overlapped the previous kernel's tail
 
   const int nW = p.nWh * p.nWw;
   const long long ld_qkv = 3LL * p.C, ld_out = p.C;
-  const float inv_scale = 1.0f / p.scale, c = p.scale * LOG2E;
+  const float c = p.scale * LOG2E;
   for (int item = blockIdx.x * WA_WARPS + warp; item < p.n_items; item += gridDim.x * WA_WARPS) {
     const int head = item % p.heads, wg = item / p.heads;
     const int b = wg / nW, w = wg - b * nW;
     const int wh = w / p.nWw, ww = w - wh * p.nWw;
+    // window class of the shift mask (vfe.py:321-339): windows of the last window row / column straddle the roll seam
     const int cls = p.shift > 0 ? ((wh == p.nWh - 1 ? 2 : 0) | (ww == p.nWw - 1 ? 1 : 0)) : 0;
     for (int i = lane; i < 49; i += 32) {
       const int r = i / 7, cc = i - r * 7;
@@ -126,19 +133,17 @@ window_attn_warp_kernel(const WinParams p) {
       if (h >= p.H) h -= p.H;
       if (x >= p.W) x -= p.W;
       rowoff[i] = (b * p.H + h) * p.W + x;
-      const int rh = (cls & 2) ? (r < 7 - p.shift ? 1 : 2) : 0, rw = (cls & 1) ? (cc < 7 - p.shift ? 1 : 2) : 0;
-      regf[i] = (float)(rh * 3 + rw);
     }
     __syncwarp();
     {  // 49 rows x (4 q + 4 k + 4 v) 16-byte chunks: 16 lanes per row, 2 rows per pass
       const int ch = lane & 15, which = ch >> 2, c4 = ch & 3;
       const bf16* src0 = p.qkv + (long long)which * p.C + head * 32 + c4 * 8;
-      bf16* dst0 = Qs + which * WA_MAT + c4 * 8;
+      bf16* dst0 = Qs + which * WA_MAT;
       if (ch < 12) {
 #pragma unroll 5
         for (int it = 0; it < 25; ++it) {
           const int row = 2 * it + (lane >> 4);
-          if (row < 49) cp_async16(dst0 + row * WA_LDS, src0 + (long long)rowoff[row] * ld_qkv);
+          if (row < 49) cp_async16(dst0 + wa_off(row, c4), src0 + (long long)rowoff[row] * ld_qkv);
         }
       }
       cp_async_wait_all();
@@ -148,8 +153,8 @@ window_attn_warp_kernel(const WinParams p) {
     uint32_t kf[7][4];  // B fragments of K^T for key tiles 0..6 (keys 0..55), both k-steps of the 32-wide head
 #pragma unroll
     for (int nt = 0; nt < 7; ++nt)
-      ldsm_x4(smem_u32(Ks + (nt * 8 + (lane & 7)) * WA_LDS + (lane >> 3) * 8), kf[nt][0], kf[nt][1], kf[nt][2], kf[nt][3]);
-    const float* rb = p.relbias + (long long)head * 4096;
+      ldsm_x4(smem_u32(Ks + wa_off(nt * 8 + (lane & 7), lane >> 3)), kf[nt][0], kf[nt][1], kf[nt][2], kf[nt][3]);
+    const float4* bt = p.bias_frag + (long long)(cls * p.heads + head) * (4 * 7 * 32) + lane;
 
 #pragma unroll 1
     for (int mt = 0; mt < 4; ++mt) {
@@ -157,25 +162,13 @@ window_attn_warp_kernel(const WinParams p) {
       uint32_t qa[2][4];
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks)
-        ldsm_x4(smem_u32(Qs + (r0 + (lane & 15)) * WA_LDS + ks * 16 + (lane >> 4) * 8), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+        ldsm_x4(smem_u32(Qs + wa_off(r0 + (lane & 15), ks * 2 + (lane >> 4))), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
       float s[7][4];
-      const float ri0 = regf[i0], ri1 = regf[i1];
 #pragma unroll
       for (int nt = 0; nt < 7; ++nt) {
-        const int j = nt * 8 + 2 * t;
-        float2 b0 = __ldg(reinterpret_cast<const float2*>(rb + i0 * 64 + j));
-        float2 b1 = __ldg(reinterpret_cast<const float2*>(rb + i1 * 64 + j));
-        if (cls) {  // warp-uniform: only windows on the last window row / column carry the -100 shift mask
-          const float2 rj = *reinterpret_cast<const float2*>(regf + j);
-          b0.x += rj.x != ri0 ? -100.f : 0.f; b0.y += rj.y != ri0 ? -100.f : 0.f;
-          b1.x += rj.x != ri1 ? -100.f : 0.f; b1.y += rj.y != ri1 ? -100.f : 0.f;
-        }
-        s[nt][0] = b0.x * inv_scale; s[nt][1] = b0.y * inv_scale;
-        s[nt][2] = b1.x * inv_scale; s[nt][3] = b1.y * inv_scale;
+        const float4 b4 = __ldg(bt + (mt * 7 + nt) * 32);
+        s[nt][0] = b4.x; s[nt][1] = b4.y; s[nt][2] = b4.z; s[nt][3] = b4.w;
       }
-      // keys 49..55 do not exist: key 48 is column 0 of the pair held by t == 0 in tile 6
-      s[6][1] = NEG_BIG; s[6][3] = NEG_BIG;
-      if (t != 0) { s[6][0] = NEG_BIG; s[6][2] = NEG_BIG; }
 #pragma unroll
       for (int nt = 0; nt < 7; ++nt) {
         mma_bf16_16816(s[nt], qa[0][0], qa[0][1], qa[0][2], qa[0][3], kf[nt][0], kf[nt][1]);
@@ -213,7 +206,7 @@ window_attn_warp_kernel(const WinParams p) {
 #pragma unroll
         for (int dp = 0; dp < 2; ++dp) {
           uint32_t b0, b1, b2, b3;
-          ldsm_x4_t(smem_u32(Vs + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * WA_LDS + dp * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
+          ldsm_x4_t(smem_u32(Vs + wa_off(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, dp * 2 + (lane >> 4))), b0, b1, b2, b3);
           mma_bf16_16816(o[2 * dp], a0, a1, a2, a3, b0, b1);
           mma_bf16_16816(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
         }
@@ -223,8 +216,8 @@ window_attn_warp_kernel(const WinParams p) {
       __syncwarp();
 #pragma unroll
       for (int dn = 0; dn < 4; ++dn) {
-        if (i0 < 49) *reinterpret_cast<uint32_t*>(Qs + i0 * WA_LDS + dn * 8 + 2 * t) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
-        if (i1 < 49) *reinterpret_cast<uint32_t*>(Qs + i1 * WA_LDS + dn * 8 + 2 * t) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
+        if (i0 < 49) *reinterpret_cast<uint32_t*>(Qs + wa_off(i0, dn) + 2 * t) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
+        if (i1 < 49) *reinterpret_cast<uint32_t*>(Qs + wa_off(i1, dn) + 2 * t) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
       }
     }
     __syncwarp();
@@ -234,7 +227,7 @@ window_attn_warp_kernel(const WinParams p) {
       for (int it = 0; it < 7; ++it) {
         const int row = it * 8 + (lane >> 2);
         if (row < 49)
-          *reinterpret_cast<uint4*>(dst0 + (long long)rowoff[row] * ld_out) = *reinterpret_cast<const uint4*>(Qs + row * WA_LDS + (lane & 3) * 8);
+          *reinterpret_cast<uint4*>(dst0 + (long long)rowoff[row] * ld_out) = *reinterpret_cast<const uint4*>(Qs + wa_off(row, lane & 3));
       }
     }
     __syncwarp();  // the next item rewrites rowoff / Q / K / V
@@ -460,14 +453,16 @@ extern "C" int mvlt_window_attention(const void* qkv, void* out, int dtype, cons
   dim3 grid(B * (H / window) * (W / window), heads);
   if (dtype == MVLT_BF16) {
     WinParams wp;
-    wp.qkv = reinterpret_cast<const bf16*>(qkv); wp.out = reinterpret_cast<bf16*>(out); wp.relbias = relbias;
+    wp.qkv = reinterpret_cast<const bf16*>(qkv); wp.out = reinterpret_cast<bf16*>(out);
+    wp.bias_frag = reinterpret_cast<const float4*>(relbias);  // bf16 path: the fragment-layout table (see the header)
+    if ((uintptr_t)relbias & 15) return MVLT_ERR_INVALID;
     wp.H = H; wp.W = W; wp.C = C; wp.heads = heads; wp.shift = shift; wp.nWh = H / window; wp.nWw = W / window;
     wp.n_items = B * wp.nWh * wp.nWw * heads; wp.scale = scale;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ctas = (wp.n_items + WA_WARPS - 1) / WA_WARPS;
-    const int gridx = ctas < 3 * sms ? ctas : 3 * sms;  // 3 CTAs (62 KB each) are resident per SM
+    const int gridx = ctas < WA_CTAS_PER_SM * sms ? ctas : WA_CTAS_PER_SM * sms;  // 2 CTAs (98 KB, 8 warps each) per SM
     launch_k(window_attn_warp_kernel, dim3(gridx), dim3(WA_WARPS * 32), WA_WARPS * WA_WARP_BYTES, stream, wp);
   } else if (dtype == MVLT_F32) {
     const int npad = 52;

@@ -216,7 +216,9 @@ class SwinTransformer(nn.Module):
                         proj_w=wcast(blk.attn.proj.weight), proj_b=f32(blk.attn.proj.bias),
                         fc1_w=wcast(blk.mlp.fc1.weight), fc1_b=f32(blk.mlp.fc1.bias),
                         fc2_w=wcast(blk.mlp.fc2.weight), fc2_b=f32(blk.mlp.fc2.bias),
-                        relbias=blk.attn.gathered_bias()))
+                        relbias=(ops.window_bias_fragments(blk.attn.gathered_bias(), blk.shift_size, blk.attn.scale,
+                                                           blk.window_size)
+                                 if self.precision == "bf16" else blk.attn.gathered_bias())))
                 if layer.downsample is not None:
                     pk["merge"].append(dict(nw=f32(layer.downsample.norm.weight), nb=f32(layer.downsample.norm.bias),
                                             red_w=wcast(layer.downsample.reduction.weight)))

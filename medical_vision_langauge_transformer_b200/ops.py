@@ -129,11 +129,49 @@ def patch_merge_ln(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, B: 
     return out
 
 
+_NEG_BIG = -1.0e30
+
+
+def window_bias_fragments(relbias: torch.Tensor, shift: int, scale: float, window: int = 7) -> torch.Tensor:
+    """Input-independent repacking of the gathered relative-position bias [heads, 64, 64] (vfe.py:236-238) for the bf16
+    window-attention kernel: (bias + shift mask) / scale in the mma.m16n8 C-fragment order, one float4 per
+    (window class, head, 16-row query tile, 8-key tile, lane); key columns 49..55 hold -1e30 (keys that do not exist).
+    Window classes (shift > 0): bit 1 = last window row, bit 0 = last window column; the -100 mask of vfe.py:318-344
+    separates the regions either side of the roll seam inside those windows.  shift == 0 -> one class."""
+    heads, n = relbias.shape[0], window * window
+    dev = relbias.device
+    i = torch.arange(64, device=dev)
+    r, c = i // window, i % window
+    n_cls = 4 if shift > 0 else 1
+    full = torch.zeros(n_cls, heads, 64, 64, device=dev, dtype=torch.float32)
+    for cls in range(n_cls):
+        rh = torch.where(r < window - shift, 1, 2) if cls & 2 else torch.zeros_like(r)
+        rw = torch.where(c < window - shift, 1, 2) if cls & 1 else torch.zeros_like(c)
+        reg = rh * 3 + rw
+        mask = torch.where(reg[:, None] != reg[None, :], -100.0, 0.0).to(torch.float32)
+        full[cls] = (relbias + mask[None]) / scale
+    full[:, :, :, n:] = _NEG_BIG
+    full[:, :, n:, :n] = 0.0
+    lane = torch.arange(32, device=dev)
+    g, t = lane // 4, lane % 4
+    e = torch.arange(4, device=dev)
+    mt, nt = torch.arange(4, device=dev), torch.arange(7, device=dev)
+    rows = mt[:, None, None, None] * 16 + g[None, None, :, None] + (e[None, None, None, :] // 2) * 8      # [4,1,32,4]
+    cols = nt[None, :, None, None] * 8 + 2 * t[None, None, :, None] + (e[None, None, None, :] % 2)        # [1,7,32,4]
+    rows, cols = rows.expand(4, 7, 32, 4), cols.expand(4, 7, 32, 4)
+    return full[:, :, rows, cols].contiguous()          # [n_cls, heads, 4, 7, 32, 4]
+
+
 def window_attention(qkv: torch.Tensor, relbias: torch.Tensor, B: int, H: int, W: int, C: int, heads: int,
                      window: int, shift: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 qkv: relbias = gathered bias [heads, 64, 64].  bf16 qkv: relbias = window_bias_fragments(...) of it."""
     lib = _lib.ensure_init()
     assert qkv.is_contiguous() and qkv.shape == (B * H * W, 3 * C)
-    assert relbias.dtype == torch.float32 and relbias.shape == (heads, 64, 64) and relbias.is_contiguous()
+    assert relbias.dtype == torch.float32 and relbias.is_contiguous()
+    if qkv.dtype == torch.bfloat16:
+        assert relbias.shape == (4 if shift > 0 else 1, heads, 4, 7, 32, 4), "bf16 path takes window_bias_fragments()"
+    else:
+        assert relbias.shape == (heads, 64, 64)
     if out is None:
         out = torch.empty((B * H * W, C), device=qkv.device, dtype=qkv.dtype)
     rc = lib.mvlt_window_attention(qkv.data_ptr(), out.data_ptr(), _code(qkv), relbias.data_ptr(), B, H, W, C, heads,

@@ -243,7 +243,8 @@ def test_window_attention(cuda, H, C, heads, shift):
     B, qkv, relb, ref = _window_case(H, C, heads, shift, seed=H + shift)
     out = ops.window_attention(qkv, relb, B, H, H, C, heads, 7, shift, 32 ** -0.5)
     assert relerr(out.cpu(), ref) < 1e-5
-    out16 = ops.window_attention(qkv.bfloat16(), relb, B, H, H, C, heads, 7, shift, 32 ** -0.5)
+    frag = ops.window_bias_fragments(relb, shift, 32 ** -0.5)
+    out16 = ops.window_attention(qkv.bfloat16(), frag, B, H, H, C, heads, 7, shift, 32 ** -0.5)
     assert relerr(out16.cpu(), ref) < 1.5e-2
 
 
