@@ -185,19 +185,58 @@ def gemm_roofline(model, x, ids, pk, steps=3):
     finally:
         ops.linear = orig
     last = per_step[1:]                                                     # drop the first (cold) pass
-    t = sum(sum(r[0] for r in st) for st in last) / len(last)
+    t_eager = sum(sum(r[0] for r in st) for st in last) / len(last)
     fl = sum(r[1] for r in last[0])
     by_shape = {}
     for st in last:
         for dt, f, shp in st:
             d = by_shape.setdefault(shp, [0.0, 0.0, 0])
             d[0] += dt / len(last); d[1] += f / len(last); d[2] += 1.0 / len(last)
+    # The roofline figure: the SAME launches (same arguments, same buffers, same order) replayed back to back as one CUDA
+    # graph between two events on the launching stream — the kernel timed inside a long step, free of the eager loop's
+    # per-launch event overhead.  Operands are cold (the step's activations >> L2), in-place residual outputs drift
+    # harmlessly (fp32).  The eager per-launch figures stay in gemm_by_shape / gemm_ms_per_step_eager.
+    calls = []          # (a, w, bias, act, residual, out): the tensors stay referenced, so their storage outlives the forward
+
+    def rec_linear(a, w, bias=None, act=0, residual=None, out=None, out_dtype=None, block_n=0):
+        o = orig(a, w, bias, act=act, residual=residual, out=out, out_dtype=out_dtype, block_n=block_n)
+        if a.dtype == torch.bfloat16:
+            calls.append((a, w, bias, act, residual, o, block_n))
+        return o
+
+    try:
+        ops.linear = rec_linear
+        for mod in list(sys.modules.values()):
+            if getattr(mod, "__name__", "").startswith("medical_vision_langauge_transformer_b200.modules") and hasattr(mod, "ops"):
+                mod.ops.linear = rec_linear
+        with torch.no_grad():
+            model(x, ids, None)
+        torch.cuda.synchronize()
+    finally:
+        ops.linear = orig
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st), torch.no_grad():
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for a, w, bias, act, residual, o, bn in calls:
+                orig(a, w, bias, act=act, residual=residual, out=o, block_n=bn)
+        for _ in range(3):
+            g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record(st)
+        for _ in range(reps):
+            g.replay()
+        e1.record(st)
+        st.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3 / reps
     achieved = fl / t / 1e12
     return {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
             "frac": achieved / pk["bf16_sustained"], "traffic": None,
-            "kernel": "gemm_tc_kernel (tcgen05 bf16, all nn.Linear sites)", "launches_per_step": len(last[0]),
-            "gemm_ms_per_step": t * 1e3, "gemm_flop_per_step": fl, "peak_source": pk["source"] + ", sustained figure",
-            "frac_of_burst_peak": achieved / pk["bf16_burst"]}, by_shape
+            "kernel": "gemm_tc_kernel (tcgen05 bf16, all nn.Linear sites)", "launches_per_step": len(calls),
+            "gemm_ms_per_step": t * 1e3, "gemm_ms_per_step_eager": t_eager * 1e3, "gemm_flop_per_step": fl,
+            "timing": "all GEMM launches of one step replayed back to back as a CUDA graph, 10 replays between two CUDA events",
+            "peak_source": pk["source"] + ", sustained figure", "frac_of_burst_peak": achieved / pk["bf16_burst"]}, by_shape
 
 
 def run_ours(args):
