@@ -47,16 +47,20 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 // 4 KB (32 x 128 B), and the residual variant needs a third buffer (prefetch of chunk k+1 while k-1 still drains).
 // DEEP (residual GEMMs with K >= 1024: fc2 / BERT output.dense): the MMAs of a tile take >= 6000 cycles, so four
 // epilogue warps with two buffers keep up and the ring gets its six stages back.
-template <bool OUT_BF16, bool RES, bool DEEP> struct Plan {
+// RES: 0 no residual; 1 out-of-place residual (C = acc + R, R != C: TMA-prefetched chunks added in shared memory);
+//      2 in-place residual (C += acc): the epilogue stores with cp.reduce.async.bulk.tensor .add — the fp32 add happens at
+//        the L2 and the residual never enters the SM (no prefetch, no LDS, half the epilogue's shared-memory traffic, which
+//        competes with the operand feed of the SS-mode MMAs for the same 128 B/clk port).
+template <bool OUT_BF16, int RES, bool DEEP> struct Plan {
   // bf16 outputs (qkv, fc1/FFN-in + GELU): the per-chunk chain tcgen05.ld -> bias -> GELU -> pack -> st.shared -> fence ->
   // TMA store is latency-bound with two warps per scheduler (measured 1900 cycles per 32x32 chunk for ~300 issued
   // instructions, tools/gemm_trace.py) and those call sites are epilogue-bound: 16 warps = four per scheduler.
-  static constexpr int EPI_WARPS = DEEP ? 4 : (OUT_BF16 ? 16 : 8);
+  static constexpr int EPI_WARPS = RES == 2 ? (DEEP ? 8 : 16) : (DEEP ? 4 : (OUT_BF16 ? 16 : 8));
   static constexpr int THREADS = (4 + EPI_WARPS) * 32;       // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare
   static constexpr int EPI_PARTS = EPI_WARPS / 4;            // warps per TMEM lane quarter
   // staging buffers per warp: the residual variant prefetches chunk k+1 while k-1 still drains (3; DEEP: 2); with four
   // warps per scheduler a single buffer is enough — its previous store drains during the next chunk's tcgen05.ld + math
-  static constexpr int NBUF = RES ? (DEEP ? 2 : 3) : (OUT_BF16 ? 1 : 2);
+  static constexpr int NBUF = RES == 1 ? (DEEP ? 2 : 3) : ((OUT_BF16 || RES == 2) ? 1 : 2);
   static constexpr int BUF_BYTES = OUT_BF16 ? 2048 : 4096;
   static constexpr int STAGING_BYTES = EPI_WARPS * NBUF * BUF_BYTES;
   static constexpr int EPI_BYTES = STAGING_BYTES + EPI_WARPS * 128;   // + one 32-float bias slot per warp
@@ -67,7 +71,7 @@ template <bool OUT_BF16, bool RES, bool DEEP> struct Plan {
   static constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + AUX_BYTES + 1024 /*align slack*/;
   static_assert(NUM_BARS * 8 + 8 <= AUX_BYTES, "barrier block too small");
   static_assert(SMEM_BYTES <= SMEM_LIMIT && STAGES >= 4 && THREADS <= 1024, "shared memory budget");
-  static_assert(!DEEP || RES, "DEEP is a residual-variant plan");
+  static_assert(!DEEP || RES != 0, "DEEP is a residual-variant plan");
 };
 
 struct GemmParams {
@@ -121,12 +125,12 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-// ACT: 0 none, 1 erf-GELU, 2 tanh.  OUT_BF16: C is bf16 (else fp32).  RES: C += residual (fp32, via tmap_r; fp32 C only).
-template <int ACT, bool OUT_BF16, bool RES, bool DEEP>
+// ACT: 0 none, 1 erf-GELU, 2 tanh.  OUT_BF16: C is bf16 (else fp32).  RES: see Plan (fp32 C only).
+template <int ACT, bool OUT_BF16, int RES, bool DEEP>
 __global__ void __launch_bounds__((Plan<OUT_BF16, RES, DEEP>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, GemmParams p) {
-  static_assert(!(RES && OUT_BF16), "residual epilogue is fp32-in/fp32-out");
+  static_assert(!(RES != 0 && OUT_BF16), "residual epilogue is fp32-in/fp32-out");
   using P = Plan<OUT_BF16, RES, DEEP>;
   constexpr int STAGES = P::STAGES, EPI_NBUF = P::NBUF, EPI_BUF_BYTES = P::BUF_BYTES, RING_BYTES = P::RING_BYTES;
   constexpr int EPI_BYTES = P::EPI_BYTES, NUM_BARS = P::NUM_BARS, NUM_EPI_WARPS = P::EPI_WARPS, EPI_PARTS = P::EPI_PARTS;
@@ -157,7 +161,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_c);
-    if (RES) tma_prefetch_desc(&tmap_r);
+    if (RES == 1) tma_prefetch_desc(&tmap_r);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -289,7 +293,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tile_origin(cur);
     normalize(cur);
     float bias_next = cur.ti < my_tiles ? bias_fetch(cur.n0t + cur.c * 32) : 0.f;
-    if (RES) {
+    if (RES == 1) {
       if (cur.ti < my_tiles) {
         const int m0 = cur.m0, n0 = cur.n0t + cur.c * 32;
         if (n0 < p.N && m0 < p.M && elect_one()) {
@@ -330,7 +334,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (has_next) bias_next = bias_fetch(n1);
       // at most the store of step k-1 is still reading shared memory.  3 buffers (RES): buffer (k+1) % 3, last used by
       // step k-2, is free for the next residual chunk; 2 buffers: buffer k % 2 (step k-2) is free for this step's writes
-      if (RES && elect_one()) {
+      if (RES == 1 && elect_one()) {
         // at most the store of step k-1 is still reading shared memory: buffer (k+1) % 3, last used by step k-2, is free
         // for the next residual chunk.  DEEP (2 buffers): the prefetch target was step k-1's buffer -> drain everything
         if (EPI_NBUF == 2) bulk_wait_read<0>(); else bulk_wait_read<1>();
@@ -353,7 +357,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (live) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_lane + (uint32_t)((ti & 1) * BN_MAX + c * 32), r);
-        if (RES) {
+        if (RES == 1) {
           mbar_wait(&rbar[buf], (res_parity >> buf) & 1);
           res_parity ^= 1u << buf;
         }
@@ -378,7 +382,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int i = 0; i < 16; ++i) v[i] = make_float2(tanhf(v[i].x), tanhf(v[i].y));
         }
         if (tr_on) GEMM_STAMP(256 + 8 * k + 4);
-        if (!RES) {  // buffer k % NBUF was last read by the store of step k - NBUF
+        if (RES != 1) {  // buffer k % NBUF was last read by the store of step k - NBUF
           if (elect_one()) bulk_wait_read<EPI_NBUF - 1>();
           __syncwarp();
         }
@@ -391,14 +395,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                            pack_bf16x2(v[4 * j + 2].x, v[4 * j + 2].y), pack_bf16x2(v[4 * j + 3].x, v[4 * j + 3].y));
         } else {
           float4 t[8];
-          if (RES) {  // all eight loads before the first store: the in-place slots alias as far as the compiler can tell
+          if (RES == 1) {  // all eight loads before the first store: the in-place slots alias as far as the compiler can tell
 #pragma unroll
             for (int j = 0; j < 8; ++j) t[j] = *reinterpret_cast<const float4*>(sb + row_base + (((uint32_t)j ^ swz) << 4));
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float2 a = v[2 * j], b = v[2 * j + 1];
-            if (RES) {
+            if (RES == 1) {
               a = add2(a, make_float2(t[j].x, t[j].y));
               b = add2(b, make_float2(t[j].z, t[j].w));
             }
@@ -411,7 +415,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       __syncwarp();
       if (tr_on) GEMM_STAMP(256 + 8 * k + 6);
       if (elect_one()) {
-        if (live) tma_store_2d(&tmap_c, sb, n0, m0);
+        if (live) {
+          if (RES == 2) tma_reduce_add_2d(&tmap_c, sb, n0, m0); else tma_store_2d(&tmap_c, sb, n0, m0);
+        }
         bulk_commit();  // one group per step (empty when the chunk lies beyond N) keeps the wait_group arithmetic uniform
       }
       __syncwarp();
@@ -446,35 +452,22 @@ static int g_num_sms = 0;
 
 typedef void (*GemmKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, GemmParams);
 
-static int smem_bytes(bool out_bf16, bool res, bool deep) {
-  return out_bf16 ? Plan<true, false, false>::SMEM_BYTES
-                  : res ? (deep ? Plan<false, true, true>::SMEM_BYTES : Plan<false, true, false>::SMEM_BYTES)
-                        : Plan<false, false, false>::SMEM_BYTES;
+struct Variant {
+  GemmKernel kernel;
+  int smem, threads;
+};
+template <int ACT, bool OUT_BF16, int RES, bool DEEP> static Variant variant() {
+  using P = Plan<OUT_BF16, RES, DEEP>;
+  return Variant{gemm_tc_kernel<ACT, OUT_BF16, RES, DEEP>, P::SMEM_BYTES, P::THREADS};
 }
-
-static GemmKernel pick_kernel(int act, bool out_bf16, bool res, bool deep) {
-#define MVLT_K(A, O, R, D) gemm_tc_kernel<A, O, R, D>
-  if (out_bf16) {
-    switch (act) {
-      case 0: return MVLT_K(0, true, false, false);
-      case 1: return MVLT_K(1, true, false, false);
-      default: return MVLT_K(2, true, false, false);
-    }
-  }
-  if (res) {
-    if (deep) return MVLT_K(0, false, true, true);  // act == 0 only (checked by the caller)
-    switch (act) {
-      case 0: return MVLT_K(0, false, true, false);
-      case 1: return MVLT_K(1, false, true, false);
-      default: return MVLT_K(2, false, true, false);
-    }
-  }
-  switch (act) {
-    case 0: return MVLT_K(0, false, false, false);
-    case 1: return MVLT_K(1, false, false, false);
-    default: return MVLT_K(2, false, false, false);
-  }
-#undef MVLT_K
+// act 0..2; res 0..2; deep only with res != 0 and act == 0 (checked by the caller)
+static Variant pick_variant(int act, bool out_bf16, int res, bool deep) {
+#define MVLT_ACT(O, R, D) (act == 0 ? variant<0, O, R, D>() : act == 1 ? variant<1, O, R, D>() : variant<2, O, R, D>())
+  if (out_bf16) return MVLT_ACT(true, 0, false);
+  if (res == 1) return deep ? variant<0, false, 1, true>() : MVLT_ACT(false, 1, false);
+  if (res == 2) return deep ? variant<0, false, 2, true>() : MVLT_ACT(false, 2, false);
+  return MVLT_ACT(false, 0, false);
+#undef MVLT_ACT
 }
 
 static int gemm_tc_init() {
@@ -485,11 +478,11 @@ static int gemm_tc_init() {
   if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return MVLT_ERR_DRIVER;
   for (int act = 0; act < 3; ++act)
     for (int o = 0; o < 2; ++o)
-      for (int r = 0; r < 2; ++r)
+      for (int r = 0; r < 3; ++r)
         for (int d = 0; d < 2; ++d) {
           if ((o && r) || (d && (!r || act != 0))) continue;
-          e = cudaFuncSetAttribute(pick_kernel(act, o != 0, r != 0, d != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   smem_bytes(o != 0, r != 0, d != 0));
+          const Variant v = pick_variant(act, o != 0, r, d != 0);
+          e = cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem);
           if (e != cudaSuccess) return (int)e;
         }
   int dev = 0;
@@ -596,8 +589,11 @@ extern "C" int mvlt_gemm_bf16_tc(const void* A, long long lda, const void* W, lo
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   const bool deep = res && act == 0 && K >= 1024;
-  cfg.blockDim = dim3(out_bf16 ? Plan<true, false, false>::THREADS : (deep ? Plan<false, true, true>::THREADS : Plan<false, false, false>::THREADS));
-  cfg.dynamicSmemBytes = smem_bytes(out_bf16, res, deep);
+  // in place (C is the residual): reduce-add stores; anything else: TMA-prefetched residual chunks
+  const int res_mode = !res ? 0 : ((residual == C && ldres == ldc) ? 2 : 1);
+  const Variant var = pick_variant(act, out_bf16, res_mode, deep);
+  cfg.blockDim = dim3(var.threads);
+  cfg.dynamicSmemBytes = var.smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -608,6 +604,6 @@ extern "C" int mvlt_gemm_bf16_tc(const void* A, long long lda, const void* W, lo
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = mvlt_pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, pick_kernel(act, out_bf16, res, deep), ta, tb, tc, tr, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, var.kernel, ta, tb, tc, tr, p);
   return e == cudaSuccess ? MVLT_OK : (int)e;
 }

@@ -191,12 +191,14 @@ class MVLBert(_PackedMixin, nn.Module):
         for li, w in enumerate(pk["layers"]):
             qkv = ops.linear(hb if bf else h, w["qkv_w"], w["qkv_b"])
             ctx = ops.joint_attention(qkv, kmask, B, S, heads, bool(seq2seq_mask), n_obj + 1)
-            y = ops.linear(ctx, w["ao_w"], w["ao_b"], residual=h, out_dtype=torch.float32)
-            h1 = ops.layernorm(y, w["ln1_w"], w["ln1_b"], eps, torch.float32, bf16_copy=bf)
+            # residual GEMMs accumulate IN PLACE into the fp32 hidden state (the tcgen05 epilogue reduce-adds its tile at the
+            # L2, the residual never enters the SM); each LayerNorm then rewrites the rows it has just read
+            ops.linear(ctx, w["ao_w"], w["ao_b"], residual=h, out=h)
+            h1 = ops.layernorm(h, w["ln1_w"], w["ln1_b"], eps, torch.float32, out=h, bf16_copy=bf)
             h1, h1b = h1 if bf else (h1, None)
             f = ops.linear(h1b if bf else h1, w["fi_w"], w["fi_b"], act=ops.ACT_GELU)
-            y = ops.linear(f, w["fo_w"], w["fo_b"], residual=h1, out_dtype=torch.float32, out=y)
-            h = ops.layernorm(y, w["ln2_w"], w["ln2_b"], eps, torch.float32, out=h, bf16_copy=bf)
+            ops.linear(f, w["fo_w"], w["fo_b"], residual=h1, out=h1)
+            h = ops.layernorm(h1, w["ln2_w"], w["ln2_b"], eps, torch.float32, out=h1, bf16_copy=bf)
             h, hb = h if bf else (h, None)
             if taps is not None and li in (0, len(pk["layers"]) - 1):
                 taps[f"bert{li}"] = h.clone().view(B, S, -1)
