@@ -11,7 +11,7 @@
 //        MMA2(j): acc2 (TMEM, C cols)       += A2[j&1][128,64] . W2[:, 64j:64j+64]^T    (W2 tiles [64,64], same ring)
 //      issue order MMA1(0), MMA1(1), MMA2(0), MMA1(2), MMA2(1), ...: the tensor pipe works on chunk j+1 while the
 //      epilogue warps run GELU on chunk j (acc1 and A2 double-buffered).
-//   3. warps 2-9: tcgen05.ld acc2 -> +b2 -> + x (re-read, L2 hit) -> x.
+//   3. warps 2-9: tcgen05.ld acc2 -> +b2 -> shared memory -> TMA reduce-add into x (the residual add happens at the L2).
 // HBM traffic is the algorithmic minimum (x read once + written once, weights from L2); compared with the unfused
 // LN -> GEMM(GELU) -> GEMM(+res) chain it removes the bf16 LN output (2C B/row), the hidden write + read (16C B/row)
 // and two launches per block.  Roles: warp 0 TMA producer (+ barrier init), warp 1 TMEM allocator + MMA issuer.
@@ -143,7 +143,8 @@ __device__ __forceinline__ void mlp_ln_rows(const MlpParams& p, long long row0, 
 
 template <int C>
 __global__ void __launch_bounds__(MLP_THREADS, MlpPlan<C>::MIN_CTAS)
-swin_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2, MlpParams p) {
+swin_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
+                const __grid_constant__ CUtensorMap tmap_x, MlpParams p) {
   using P = MlpPlan<C>;
   constexpr int KB1 = P::KB1, NCHUNK = P::NCHUNK, NT2 = P::NT2, NSLOT = P::NSLOT, SLOT = P::SLOT;
   extern __shared__ uint8_t smem_raw[];
@@ -168,6 +169,7 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_w1);
     tma_prefetch_desc(&tmap_w2);
+    tma_prefetch_desc(&tmap_x);
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     mbar_init(a1_full, 8);
     for (int b = 0; b < 2; ++b) { mbar_init(&acc1_full[b], 1); mbar_init(&a2_full[b], 8); mbar_init(&a2_empty[b], 1); }
@@ -321,35 +323,39 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_consta
       if (ew == 0) MLP_STAMP(256 + 4 * j + 3);
     }
 
-    // final epilogue: acc2 + b2 + x -> x
+    // final epilogue: x += acc2 + b2.  Each warp parks its 32x32 fp32 chunk in shared memory (A1 is dead: every MMA1 has
+    // retired) in the TMA swizzle pattern and stores it with cp.reduce.async.bulk.tensor .add: the residual add happens at
+    // the L2, x is never re-read by the SM, rows past M are clipped by the TMA unit.
     mbar_wait(acc2_full, 0);
     tc_fence_after();
     if (ew == 0) MLP_STAMP(5);
-    const long long row = row0 + r;
-    float* xrow = p.x + row * p.ldx;
+    uint8_t* sb = a1 + ew * 4096;
+    const uint32_t srow = (uint32_t)lane * 128u, sswz = (uint32_t)lane & 7u;
 #pragma unroll 1
     for (int c = part; c < C / 32; c += 2) {
       uint32_t rg[32];
       tmem_ld_32x32(tmem_lane + c * 32, rg);
-      float4 res[8];
-      if (row < p.M) {
+      float4 bb[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) res[i] = *(reinterpret_cast<const float4*>(xrow + c * 32) + i);
-      }
+      for (int i = 0; i < 8; ++i) bb[i] = __ldg(reinterpret_cast<const float4*>(p.b2 + c * 32) + i);
+      if (elect_one()) bulk_wait_read<0>();   // this warp's previous store has left its staging buffer
+      __syncwarp();
       tmem_ld_wait();
-      if (row < p.M) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + c * 32) + i);
-          float4 o;
-          o.x = __uint_as_float(rg[4 * i]) + bb.x + res[i].x;
-          o.y = __uint_as_float(rg[4 * i + 1]) + bb.y + res[i].y;
-          o.z = __uint_as_float(rg[4 * i + 2]) + bb.z + res[i].z;
-          o.w = __uint_as_float(rg[4 * i + 3]) + bb.w + res[i].w;
-          *(reinterpret_cast<float4*>(xrow + c * 32) + i) = o;
-        }
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(sb + srow + (((uint32_t)i ^ sswz) << 4)) =
+            make_float4(__uint_as_float(rg[4 * i]) + bb[i].x, __uint_as_float(rg[4 * i + 1]) + bb[i].y,
+                        __uint_as_float(rg[4 * i + 2]) + bb[i].z, __uint_as_float(rg[4 * i + 3]) + bb[i].w);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (elect_one()) {
+        tma_reduce_add_2d(&tmap_x, sb, c * 32, (int)(row0 + quarter * 32));
+        bulk_commit();
       }
+      __syncwarp();
     }
+    if (elect_one()) bulk_wait_all();
+    __syncwarp();
   }
 
   if (warp == MLP_EPI_WARP0) MLP_STAMP(6);
@@ -376,8 +382,11 @@ static int launch_swin_mlp(const MlpParams& p, const void* w1, const void* w2, c
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != MVLT_OK) return rc;
   if ((rc = make_tmap(&t2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w2, C, P::HID, P::HID, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != MVLT_OK) return rc;
+  CUtensorMap tx;
+  if ((rc = make_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.x, p.M, C, p.ldx, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_NONE)) != MVLT_OK) return rc;
   const long long tiles = (p.M + MLP_BM - 1) / MLP_BM;
-  cudaError_t e = launch_k(swin_mlp_kernel<C>, dim3((unsigned)tiles), dim3(MLP_THREADS), (size_t)P::SMEM_BYTES, stream, t1, t2, p);
+  cudaError_t e = launch_k(swin_mlp_kernel<C>, dim3((unsigned)tiles), dim3(MLP_THREADS), (size_t)P::SMEM_BYTES, stream, t1, t2, tx, p);
   return e == cudaSuccess ? MVLT_OK : (int)e;
 }
 

@@ -237,10 +237,12 @@ class SwinTransformer(nn.Module):
         adt = act_dtype(self.precision)
         x = x.contiguous().float()
         X = ops.patch_embed_ln(x, pk["pe_w"], pk["pe_b"], pe.norm.weight, pe.norm.bias, pe.norm.eps)
-        # MVLT_FUSED_MLP=1 (experimental, bf16 mode): LN2 + fc1 + GELU + fc2 + residual as ONE kernel (csrc/swin_mlp.cu) for the
-        # stage widths whose fc2 accumulator fits TMEM.  Parity-green but shared-memory-bandwidth bound at N=64 MMAs (84 us vs
-        # 51 us for the unfused chain at stage 2), so the unfused kernels stay the default.
-        fused_mlp = self.precision == "bf16" and os.environ.get("MVLT_FUSED_MLP", "0") == "1"
+        # LN2 + fc1 + GELU + fc2 + residual as ONE tcgen05 kernel (csrc/swin_mlp.cu) for the stage widths listed in
+        # MVLT_FUSED_MLP (bf16 mode).  Default: stage 0 only (C = 96, HBM-bound: 96 us vs 136 us for the unfused chain);
+        # at C = 192 / 384 the kernel is shared-memory-bandwidth bound at its N = 64 MMAs and the unfused chain is faster
+        # (profiles/r01_fused_mlp_vs_chain.log), "96,192,384" enables it everywhere, "" nowhere.
+        fused_widths = tuple(int(v) for v in os.environ.get("MVLT_FUSED_MLP", "96").split(",") if v.strip()) \
+            if self.precision == "bf16" else ()
         taps = self.taps
         if taps is not None:
             taps["patch_embed"] = X.clone().view(B, -1, X.shape[-1])
@@ -257,7 +259,7 @@ class SwinTransformer(nn.Module):
                 o = ops.window_attention(qkv, w["relbias"], B, H, W, C, blk.num_heads, blk.window_size, blk.shift_size,
                                          blk.attn.scale)
                 ops.linear(o, w["proj_w"], w["proj_b"], residual=X, out=X)
-                if fused_mlp and C in ops.FUSED_MLP_WIDTHS and w["fc1_w"].shape[0] == 4 * C:
+                if C in fused_widths and C in ops.FUSED_MLP_WIDTHS and w["fc1_w"].shape[0] == 4 * C:
                     ops.swin_mlp(X, w["n2w"], w["n2b"], blk.norm2.eps, w["fc1_w"], w["fc1_b"], w["fc2_w"], w["fc2_b"])
                 else:
                     a = ops.layernorm(X, w["n2w"], w["n2b"], blk.norm2.eps, adt)
