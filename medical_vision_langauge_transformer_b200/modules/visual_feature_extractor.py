@@ -236,7 +236,8 @@ class SwinTransformer(nn.Module):
         pk = self.packed()
         adt = act_dtype(self.precision)
         x = x.contiguous().float()
-        X = ops.patch_embed_ln(x, pk["pe_w"], pk["pe_b"], pe.norm.weight, pe.norm.bias, pe.norm.eps)
+        X = ops.patch_embed_ln(x, pk["pe_w"], pk["pe_b"], pe.norm.weight, pe.norm.bias, pe.norm.eps,
+                               tensor_cores=self.precision == "bf16")
         # LN2 + fc1 + GELU + fc2 + residual as ONE tcgen05 kernel (csrc/swin_mlp.cu) for the stage widths listed in
         # MVLT_FUSED_MLP (bf16 mode).  Default: stage 0 only (C = 96, HBM-bound: 96 us vs 136 us for the unfused chain);
         # at C = 192 / 384 the kernel is shared-memory-bandwidth bound at its N = 64 MMAs and the unfused chain is faster

@@ -186,9 +186,11 @@ def test_patch_embed(cuda):
         img = rnd(3, 3, 224, 224, seed=1, scale=scale)
         sd = {"proj.weight": rnd(96, 3, 4, 4, seed=2, scale=0.1), "proj.bias": rnd(96, seed=3, scale=0.02),
               "norm.weight": 1 + rnd(96, seed=4, scale=0.1), "norm.bias": rnd(96, seed=5, scale=0.05)}
-        out = ops.patch_embed_ln(img, sd["proj.weight"], sd["proj.bias"], sd["norm.weight"], sd["norm.bias"])
         ref = O.patch_embed({k: v.cpu() for k, v in sd.items()}, "", img.cpu())
-        assert relerr(out.view(3, 3136, 96).cpu(), ref) < 1e-5
+        for tc in (False, True):   # fp32 CUDA-core kernel; tensor-core kernel with bf16 hi/lo operand splitting
+            out = ops.patch_embed_ln(img, sd["proj.weight"], sd["proj.bias"], sd["norm.weight"], sd["norm.bias"],
+                                     tensor_cores=tc)
+            assert relerr(out.view(3, 3136, 96).cpu(), ref) < 1e-5, (scale, tc)
 
 
 @pytest.mark.parametrize("H,C", [(56, 96), (28, 192), (14, 384)])
