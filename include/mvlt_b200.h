@@ -75,7 +75,9 @@ int mvlt_patch_embed_ln(const float* img, const float* weight, const float* bias
  * fp32-accurate (~1e-6 relative).  The bf16-mode stem: 5x faster than the FMA-bound kernel above. */
 int mvlt_patch_embed_ln_tc(const float* img, const float* weight, const float* bias, const float* gamma,
                            const float* beta, float* out, int B, int img_size, int patch, int embed_dim, float eps,
-                           mvlt_stream_t stream);
+                           const float* gamma2, const float* beta2, float eps2, void* out2_bf16, mvlt_stream_t stream);
+/* out2_bf16 (or NULL): additionally LayerNorm(out; gamma2, beta2, eps2) rounded to bf16 [B*3136, 96] — norm1 of the first
+ * Swin block (vfe.py:356) computed on the rows while they are still in registers. */
 
 /* PatchMerging gather + LayerNorm(4C): x fp32 [B,H,W,C] -> out [B*H/2*W/2, 4C] in quad order (0,0),(1,0),(0,1),(1,1).
  * vfe.py:433-442 (the Linear(4C,2C) that follows is mvlt_gemm_*). */

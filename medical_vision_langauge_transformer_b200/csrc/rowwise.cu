@@ -70,6 +70,58 @@ layernorm_rows_kernel(const TI* __restrict__ in, long long ld_in, TO* __restrict
                    threadIdx.x & 31, out_copy ? out_copy + row * ld_copy : nullptr);
 }
 
+// Narrow rows (C % 32 == 0, C <= 128: Swin stage 0): eight lanes per row, four rows per warp, so every lane of the warp
+// carries loads (one warp per 96-wide row leaves a quarter of the lanes idle and the kernel at half of HBM speed).
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+layernorm_rows_small_kernel(const TI* __restrict__ in, long long ld_in, TO* __restrict__ out, long long ld_out,
+                            const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, int C, float eps,
+                            int gelu, bf16* __restrict__ out_copy, long long ld_copy) {
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31, sub = lane & 7;
+  const long long row = (long long)blockIdx.x * 32 + (threadIdx.x >> 5) * 4 + (lane >> 3);
+  const bool live = row < rows;
+  const int nq = C >> 5;  // quads per lane
+  const TI* src = in + (live ? row : 0) * ld_in;
+  float4 v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < nq) {
+      v[i] = load4(src + (sub + 8 * i) * 4);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < nq) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
+  const float rstd = 1.0f / sqrtf(q / (float)C + eps);
+  if (!live) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < nq) {
+      const int c = (sub + 8 * i) * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (gelu) {
+        o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w);
+      }
+      store4(out + row * ld_out + c, o);
+      if (out_copy) store4(out_copy + row * ld_copy + c, o);
+    }
+}
+
 // out row (b, h2, w2) = LN( cat[x(2h2,2w2), x(2h2+1,2w2), x(2h2,2w2+1), x(2h2+1,2w2+1)] ), x fp32 [B,H,W,C]
 template <int NCH, typename TO>
 __global__ void __launch_bounds__(256)
@@ -178,11 +230,13 @@ __device__ __forceinline__ void pt_split(float2 x, uint32_t& hi, uint32_t& lo) {
 __global__ void __launch_bounds__(PT_WARPS * 32, 3)
 patch_embed_ln_tc_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
                          const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
-                         float eps, int n_groups) {
+                         float eps, int n_groups, const float* __restrict__ gamma2, const float* __restrict__ beta2,
+                         float eps2, bf16* __restrict__ out2) {
   __shared__ __align__(16) bf16 w_hi[PE_C * PT_LDW];
   __shared__ __align__(16) bf16 w_lo[PE_C * PT_LDW];
   __shared__ __align__(16) float4 s_gb[PE_C / 2];   // (gamma[c], gamma[c+1], beta[c], beta[c+1]) for even c
   __shared__ __align__(8) float2 s_bias[PE_C / 2];
+  __shared__ __align__(16) float4 s_gb2[PE_C / 2];  // norm1 of the first Swin block (optional second output)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   for (int i = tid; i < PE_C * PE_K; i += PT_WARPS * 32) {   // parameters are static: staged before the PDL wait
     const int n = i / PE_K, k = i - n * PE_K;
@@ -194,6 +248,7 @@ patch_embed_ln_tc_kernel(const float* __restrict__ img, const float* __restrict_
   for (int i = tid; i < PE_C / 2; i += PT_WARPS * 32) {
     s_gb[i] = make_float4(gamma[2 * i], gamma[2 * i + 1], beta[2 * i], beta[2 * i + 1]);
     s_bias[i] = make_float2(bias[2 * i], bias[2 * i + 1]);
+    if (out2) s_gb2[i] = make_float4(gamma2[2 * i], gamma2[2 * i + 1], beta2[2 * i], beta2[2 * i + 1]);
   }
   __syncthreads();
   pdl_grid_sync();
@@ -265,8 +320,35 @@ patch_embed_ln_tc_kernel(const float* __restrict__ img, const float* __restrict_
 #pragma unroll
     for (int nt = 0; nt < 12; ++nt) {
       const float4 gb = s_gb[nt * 4 + t];
-      *reinterpret_cast<float2*>(dst[0] + nt * 8) = make_float2(acc[nt][0] * r0 * gb.x + gb.z, acc[nt][1] * r0 * gb.y + gb.w);
-      *reinterpret_cast<float2*>(dst[1] + nt * 8) = make_float2(acc[nt][2] * r1 * gb.x + gb.z, acc[nt][3] * r1 * gb.y + gb.w);
+      acc[nt][0] = acc[nt][0] * r0 * gb.x + gb.z; acc[nt][1] = acc[nt][1] * r0 * gb.y + gb.w;
+      acc[nt][2] = acc[nt][2] * r1 * gb.x + gb.z; acc[nt][3] = acc[nt][3] * r1 * gb.y + gb.w;
+      *reinterpret_cast<float2*>(dst[0] + nt * 8) = make_float2(acc[nt][0], acc[nt][1]);
+      *reinterpret_cast<float2*>(dst[1] + nt * 8) = make_float2(acc[nt][2], acc[nt][3]);
+    }
+    if (out2) {  // norm1 of block 0 on the rows still in registers (vfe.py:356): the first LayerNorm launch of the trunk
+      float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 12; ++nt) { u0 += acc[nt][0] + acc[nt][1]; u1 += acc[nt][2] + acc[nt][3]; }
+      u0 += __shfl_xor_sync(0xffffffffu, u0, 1); u0 += __shfl_xor_sync(0xffffffffu, u0, 2);
+      u1 += __shfl_xor_sync(0xffffffffu, u1, 1); u1 += __shfl_xor_sync(0xffffffffu, u1, 2);
+      const float n0 = u0 * (1.0f / PE_C), n1 = u1 * (1.0f / PE_C);
+      float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 12; ++nt) {
+        acc[nt][0] -= n0; acc[nt][1] -= n0; acc[nt][2] -= n1; acc[nt][3] -= n1;
+        p0 += acc[nt][0] * acc[nt][0] + acc[nt][1] * acc[nt][1];
+        p1 += acc[nt][2] * acc[nt][2] + acc[nt][3] * acc[nt][3];
+      }
+      p0 += __shfl_xor_sync(0xffffffffu, p0, 1); p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
+      p1 += __shfl_xor_sync(0xffffffffu, p1, 1); p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+      const float z0 = 1.0f / sqrtf(p0 * (1.0f / PE_C) + eps2), z1 = 1.0f / sqrtf(p1 * (1.0f / PE_C) + eps2);
+      bf16* d0 = out2 + (dst[0] - out), * d1 = out2 + (dst[1] - out);
+#pragma unroll
+      for (int nt = 0; nt < 12; ++nt) {
+        const float4 gb = s_gb2[nt * 4 + t];
+        *reinterpret_cast<uint32_t*>(d0 + nt * 8) = pack_bf16x2(acc[nt][0] * z0 * gb.x + gb.z, acc[nt][1] * z0 * gb.y + gb.w);
+        *reinterpret_cast<uint32_t*>(d1 + nt * 8) = pack_bf16x2(acc[nt][2] * z1 * gb.x + gb.z, acc[nt][3] * z1 * gb.y + gb.w);
+      }
     }
   }
 }
@@ -333,6 +415,11 @@ joint_embed_kernel(const TF* __restrict__ feat, const int* __restrict__ img_inde
 template <typename TI, typename TO>
 static int launch_ln(const void* in, long long ld_in, void* out, long long ld_out, const float* gamma, const float* beta,
                      long long rows, int C, float eps, int gelu, void* out_copy, long long ld_copy, cudaStream_t st) {
+  if (C <= 128 && C % 32 == 0) {
+    launch_k(layernorm_rows_small_kernel<TI, TO>, dim3((unsigned)((rows + 31) / 32)), dim3(256), 0, st, (const TI*)in, ld_in,
+             (TO*)out, ld_out, gamma, beta, rows, C, eps, gelu, (bf16*)out_copy, ld_copy);
+    return MVLT_OK;
+  }
   const unsigned grid = (unsigned)((rows + 7) / 8);
 #define LN_CASE(NCH)                                                                                              \
   launch_k(layernorm_rows_kernel<NCH, TI, TO>, dim3(grid), dim3(256), 0, st, (const TI*)in, ld_in, (TO*)out, ld_out, gamma, beta, \
@@ -381,8 +468,10 @@ extern "C" int mvlt_patch_embed_ln(const float* img, const float* weight, const 
 // Same contract on the tensor cores (bf16-mode stem; fp32-level accuracy through bf16 hi/lo operand splitting).
 extern "C" int mvlt_patch_embed_ln_tc(const float* img, const float* weight, const float* bias, const float* gamma,
                                       const float* beta, float* out, int B, int img_size, int patch, int embed_dim,
-                                      float eps, cudaStream_t stream) {
+                                      float eps, const float* gamma2, const float* beta2, float eps2, void* out2_bf16,
+                                      cudaStream_t stream) {
   if (!img || !weight || !bias || !gamma || !beta || !out || B <= 0) return MVLT_ERR_INVALID;
+  if (out2_bf16 && (!gamma2 || !beta2 || ((uintptr_t)out2_bf16 & 3))) return MVLT_ERR_INVALID;
   if (img_size != PE_IMG || patch != 4 || embed_dim != PE_C) return MVLT_ERR_UNSUPPORTED;
   if (((uintptr_t)img & 7) || ((uintptr_t)out & 7)) return MVLT_ERR_INVALID;
   const int n_groups = B * (PE_P * PE_P / 16);
@@ -391,7 +480,7 @@ extern "C" int mvlt_patch_embed_ln_tc(const float* img, const float* weight, con
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ctas = (n_groups + PT_WARPS - 1) / PT_WARPS;
   launch_k(patch_embed_ln_tc_kernel, dim3(ctas < 3 * sms ? ctas : 3 * sms), dim3(PT_WARPS * 32), 0, stream, img, weight, bias,
-           gamma, beta, out, eps, n_groups);
+           gamma, beta, out, eps, n_groups, gamma2, beta2, eps2, reinterpret_cast<bf16*>(out2_bf16));
   MVLT_LAUNCH_CHECK();
   return MVLT_OK;
 }

@@ -236,8 +236,13 @@ class SwinTransformer(nn.Module):
         pk = self.packed()
         adt = act_dtype(self.precision)
         x = x.contiguous().float()
-        X = ops.patch_embed_ln(x, pk["pe_w"], pk["pe_b"], pe.norm.weight, pe.norm.bias, pe.norm.eps,
-                               tensor_cores=self.precision == "bf16")
+        a_first = None
+        if self.precision == "bf16":   # tensor-core stem; norm1 of block 0 comes out of the same kernel
+            b0 = self.layers[0].blocks[0]
+            X, a_first = ops.patch_embed_ln(x, pk["pe_w"], pk["pe_b"], pe.norm.weight, pe.norm.bias, pe.norm.eps,
+                                            tensor_cores=True, next_norm=(pk["blocks"][0]["n1w"], pk["blocks"][0]["n1b"], b0.norm1.eps))
+        else:
+            X = ops.patch_embed_ln(x, pk["pe_w"], pk["pe_b"], pe.norm.weight, pe.norm.bias, pe.norm.eps)
         # LN2 + fc1 + GELU + fc2 + residual as ONE tcgen05 kernel (csrc/swin_mlp.cu) for the stage widths listed in
         # MVLT_FUSED_MLP (bf16 mode).  Default: stage 0 only (C = 96, HBM-bound: 96 us vs 136 us for the unfused chain);
         # at C = 192 / 384 the kernel is shared-memory-bandwidth bound at its N = 64 MMAs and the unfused chain is faster
@@ -255,7 +260,10 @@ class SwinTransformer(nn.Module):
             for i, blk in enumerate(layer.blocks):
                 w = pk["blocks"][bi]
                 bi += 1
-                a = ops.layernorm(X, w["n1w"], w["n1b"], blk.norm1.eps, adt)
+                if a_first is not None:
+                    a, a_first = a_first, None
+                else:
+                    a = ops.layernorm(X, w["n1w"], w["n1b"], blk.norm1.eps, adt)
                 qkv = ops.linear(a, w["qkv_w"], w["qkv_b"])
                 o = ops.window_attention(qkv, w["relbias"], B, H, W, C, blk.num_heads, blk.window_size, blk.shift_size,
                                          blk.attn.scale)

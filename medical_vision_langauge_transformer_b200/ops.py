@@ -105,19 +105,31 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 
 def patch_embed_ln(img: torch.Tensor, w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
-                   eps: float = 1e-5, tensor_cores: bool = False) -> torch.Tensor:
+                   eps: float = 1e-5, tensor_cores: bool = False, next_norm=None):
     """Conv2d(3,96,k4,s4) + LayerNorm(96).  tensor_cores=True: the mma.sync kernel with bf16 hi/lo operand splitting
-    (fp32-accurate, the bf16-mode stem); False: the fp32 CUDA-core kernel (parity mode)."""
+    (fp32-accurate, the bf16-mode stem); False: the fp32 CUDA-core kernel (parity mode).
+    next_norm=(gamma2, beta2, eps2) (tensor-core kernel only): also returns LayerNorm(out; gamma2, beta2) in bf16."""
     lib = _lib.ensure_init()
     B = img.shape[0]
     assert img.dtype == torch.float32 and img.is_contiguous() and w.is_contiguous()
     E, P = w.shape[0], w.shape[-1]
     n_tok = (img.shape[-1] // P) ** 2
     out = torch.empty((B * n_tok, E), device=img.device, dtype=torch.float32)
-    fn = lib.mvlt_patch_embed_ln_tc if tensor_cores else lib.mvlt_patch_embed_ln
-    rc = fn(img.data_ptr(), w.data_ptr(), b.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), B,
-            img.shape[-1], P, E, float(eps), _stream())
-    _lib.check(rc, "mvlt_patch_embed_ln_tc" if tensor_cores else "mvlt_patch_embed_ln")
+    if tensor_cores:
+        out2 = g2 = b2 = None
+        eps2 = 0.0
+        if next_norm is not None:
+            g2, b2, eps2 = next_norm
+            out2 = torch.empty((B * n_tok, E), device=img.device, dtype=torch.bfloat16)
+        rc = lib.mvlt_patch_embed_ln_tc(img.data_ptr(), w.data_ptr(), b.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                        out.data_ptr(), B, img.shape[-1], P, E, float(eps), _ptr(g2), _ptr(b2), float(eps2),
+                                        _ptr(out2), _stream())
+        _lib.check(rc, "mvlt_patch_embed_ln_tc")
+        return (out, out2) if next_norm is not None else out
+    assert next_norm is None
+    rc = lib.mvlt_patch_embed_ln(img.data_ptr(), w.data_ptr(), b.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                 out.data_ptr(), B, img.shape[-1], P, E, float(eps), _stream())
+    _lib.check(rc, "mvlt_patch_embed_ln")
     return out
 
 

@@ -191,6 +191,11 @@ def test_patch_embed(cuda):
             out = ops.patch_embed_ln(img, sd["proj.weight"], sd["proj.bias"], sd["norm.weight"], sd["norm.bias"],
                                      tensor_cores=tc)
             assert relerr(out.view(3, 3136, 96).cpu(), ref) < 1e-5, (scale, tc)
+        g2, b2 = 1 + rnd(96, seed=6, scale=0.1), rnd(96, seed=7, scale=0.05)
+        out, a = ops.patch_embed_ln(img, sd["proj.weight"], sd["proj.bias"], sd["norm.weight"], sd["norm.bias"],
+                                    tensor_cores=True, next_norm=(g2, b2, 1e-5))
+        assert relerr(out.view(3, 3136, 96).cpu(), ref) < 1e-5
+        assert relerr(a, F.layer_norm(out, (96,), g2, b2, 1e-5)) < 1e-2          # bf16 second output
 
 
 @pytest.mark.parametrize("H,C", [(56, 96), (28, 192), (14, 384)])
