@@ -12,6 +12,10 @@
 //      issue order MMA1(0), MMA1(1), MMA2(0), MMA1(2), MMA2(1), ...: the tensor pipe works on chunk j+1 while the
 //      epilogue warps run GELU on chunk j (acc1 and A2 double-buffered).
 //   3. warps 2-9: tcgen05.ld acc2 -> +b2 -> shared memory -> TMA reduce-add into x (the residual add happens at the L2).
+// A persistent variant (one CTA per SM, dedicated LayerNorm/store warps, double-buffered A1 and acc2, the weight ring
+// running across tiles) was built and measured this round: 99-109 us at stage 0 against 96-104 us for this kernel — with
+// one CTA per SM only 8 GELU warps fit the register file and the GELU rate, not the memory phases, is the bound; it was
+// dropped.
 // HBM traffic is the algorithmic minimum (x read once + written once, weights from L2); compared with the unfused
 // LN -> GEMM(GELU) -> GEMM(+res) chain it removes the bf16 LN output (2C B/row), the hidden write + read (16C B/row)
 // and two launches per block.  Roles: warp 0 TMA producer (+ barrier init), warp 1 TMEM allocator + MMA issuer.
@@ -68,18 +72,18 @@ struct MlpParams {
 static unsigned long long* g_mlp_trace = nullptr;
 #define MLP_STAMP(idx) do { if (p.trace != nullptr && blockIdx.x == 0 && lane == 0) p.trace[(idx)] = (unsigned long long)clock64(); } while (0)
 
-// LayerNorm of the 16 rows [16 ew, 16 ew + 16) of the tile -> bf16 -> A1 (K-major, 128 B rows, 16 B slots XOR (row & 7)).
-template <int C>
+// LayerNorm of the ROWS rows [ROWS ew, ROWS ew + ROWS) of the tile -> bf16 -> A1 (K-major, 128 B rows, 16 B slots XOR (row & 7)).
+template <int C, int ROWS = 16>
 __device__ __forceinline__ void mlp_ln_rows(const MlpParams& p, long long row0, uint8_t* a1, int ew, int lane) {
   constexpr int NCH = (C / 4 + 31) / 32;
   constexpr int RU = C == 384 ? 4 : 8;   // rows in flight per warp (memory-level parallelism vs registers)
   constexpr float inv_c = 1.0f / (float)C;
 #pragma unroll 1
-  for (int rr = 0; rr < 16; rr += RU) {
+  for (int rr = 0; rr < ROWS; rr += RU) {
     float4 v[RU][NCH];
 #pragma unroll
     for (int u = 0; u < RU; ++u) {
-      const long long row = row0 + ew * 16 + rr + u;
+      const long long row = row0 + ew * ROWS + rr + u;
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
         const int c = (lane + 32 * i) * 4;
@@ -127,7 +131,7 @@ __device__ __forceinline__ void mlp_ln_rows(const MlpParams& p, long long row0, 
         const int kb = c >> 6, within = c & 63;
 #pragma unroll
         for (int u = 0; u < RU; ++u) {
-          const int r = ew * 16 + rr + u;
+          const int r = ew * ROWS + rr + u;
           const float o0 = (v[u][i].x - mean[u]) * rstd[u] * g.x + b.x;
           const float o1 = (v[u][i].y - mean[u]) * rstd[u] * g.y + b.y;
           const float o2 = (v[u][i].z - mean[u]) * rstd[u] * g.z + b.z;

@@ -123,12 +123,12 @@ def test_gemm_tc_inplace_residual_and_strided_a(cuda):
     assert relerr(out, ref) < 2e-3
 
 
-@pytest.mark.parametrize("C,M", [(96, 6272), (96, 300), (96, 1), (192, 1568), (192, 129), (384, 392), (384, 12544),
-                                 (384, 127)])
+@pytest.mark.parametrize("C,M", [(96, 6272), (96, 300), (96, 1), (96, 50000), (192, 1568), (192, 129), (192, 40001),
+                                 (384, 392), (384, 12544), (384, 127)])
 def test_swin_mlp_fused(cuda, C, M):
     """x += fc2(gelu(fc1(LN(x)))) as one kernel (vfe.py:385 + :136-139) against (a) a torch restatement that rounds the
     LN output and the hidden activation to bf16 where the kernel does and (b) the unfused kernel chain, in place, at
-    full tiles, ragged last tiles and a single row."""
+    full tiles, ragged last tiles, a single row, and (C = 96 / 192: persistent kernel) more tiles than SMs."""
     from medical_vision_langauge_transformer_b200 import ops
     x = rnd(M, C, seed=C + M) * 2 + 0.3
     g, b = 1 + rnd(C, seed=1, scale=0.1), rnd(C, seed=2, scale=0.1)
