@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--conv", default="swintransformer", choices=["swintransformer", "resnet101", "resnet50"],
+                    help="visual backbone; the headline metric is the default (Swin-S), resnet101 = BASELINE.json configs[4]")
     ap.add_argument("--no-roofline", action="store_true")
     return ap.parse_args()
 
@@ -94,7 +96,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_port_pairs_per_s(batch: int, L: int, min_seconds: float = 10.0, max_runs: int = 12):
+def cpu_port_pairs_per_s(batch: int, L: int, min_seconds: float = 10.0, max_runs: int = 12, conv: str = "swintransformer"):
     """The reference forward (oracle port, torch fp32) on the host cores: VQA forward on `batch` pairs, repeated."""
     import torch
     from medical_vision_langauge_transformer_b200 import synth
@@ -103,7 +105,7 @@ def cpu_port_pairs_per_s(batch: int, L: int, min_seconds: float = 10.0, max_runs
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     torch.manual_seed(0)
-    model = M.MVLBertForVQA(C.offline_config("vqa", max_length=L)).eval()
+    model = M.MVLBertForVQA(C.offline_config("vqa", max_length=L, conv=conv)).eval()
     sd = {k: v.detach() for k, v in model.state_dict().items()}
     x, ids = synth.synth_images(batch, 1, 0.02), synth.synth_token_ids(batch, L, 1)
     times = []
@@ -130,7 +132,7 @@ def run_reference(args):
     torch.set_num_threads(threads)
     b, L = args.cpu_sample_batch, args.max_length
     torch.manual_seed(0)
-    model = M.MVLBertForVQA(C.offline_config("vqa", max_length=L)).eval()
+    model = M.MVLBertForVQA(C.offline_config("vqa", max_length=L, conv=args.conv)).eval()
     sd = {k: v.detach() for k, v in model.state_dict().items()}
     x, ids = synth.synth_images(b, 1, 0.02), synth.synth_token_ids(b, L, 1)
     steps, warm = min(args.steps, 20), min(args.warmup, 3)
@@ -146,7 +148,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": f"vqa_fwd_b{args.batch}_L{L}_swinS_bertbase", "sample_batch": b},
+        "data": "synthetic", "config": {"workload": f"vqa_fwd_b{args.batch}_L{L}_{'swinS' if args.conv == 'swintransformer' else args.conv}_bertbase", "sample_batch": b},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
@@ -259,7 +261,7 @@ def run_ours(args):
     pk = peaks()
 
     torch.manual_seed(0)                                                     # random init of the reference architecture
-    model = M.MVLBertForVQA(C.offline_config("vqa", max_length=L)).eval().to(dev).set_precision(args.precision)
+    model = M.MVLBertForVQA(C.offline_config("vqa", max_length=L, conv=args.conv)).eval().to(dev).set_precision(args.precision)
     n_rot = 4                                                                # rotate distinct batches: inputs never L2-resident
     imgs = [synth.synth_images(B, 100 + rank * 16 + i, 0.02) for i in range(n_rot)]
     idss = [synth.synth_token_ids(B, L, 100 + rank * 16 + i) for i in range(n_rot)]
@@ -324,25 +326,27 @@ def run_ours(args):
         t_res, t_e2e, t_e2e_wall = t.tolist()
 
     roof, by_shape, cpu = None, None, None
-    if rank == 0 and not args.no_roofline and args.precision == "bf16":
+    if rank == 0 and not args.no_roofline and args.precision == "bf16" and args.conv == "swintransformer":
         roof, by_shape = gemm_roofline(model, d_imgs[0], d_ids[0], pk)
         prof = os.path.join(ROOT, "profiles", "gemm_tc_traffic.json")
         if os.path.exists(prof):
             roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, sample = cpu_port_pairs_per_s(args.cpu_sample_batch, L)
+        v, cores, sample = cpu_port_pairs_per_s(args.cpu_sample_batch, L, conv=args.conv)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
         pairs = world * B * args.steps
         value = pairs / t_res
-        flop_pair = O.flops_per_pair(L) - 2 * 768 * 768 + 2 * 768 * 224           # pooler + Linear(768,224) instead of pooler + transform
+        flop_pair = O.flops_per_pair(L, args.conv) - 2 * 768 * 768 + 2 * 768 * 224  # pooler + Linear(768,224) instead of pooler + transform
+        trunk = {"swintransformer": "swinS", "resnet101": "resnet101", "resnet50": "resnet50"}[args.conv]
+        cfg_name = "configs[1] at the metric's L=80" if args.conv == "swintransformer" else "configs[4] backbone variant"
         out_bytes = sum(o.numel() * o.element_size() for o in runner.static_out[0])
         res = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"vqa_fwd_b{B}_L{L}_swinS_bertbase (BASELINE.json configs[1] at the metric's L=80)",
+            "config": {"workload": f"vqa_fwd_b{B}_L{L}_{trunk}_bertbase (BASELINE.json {cfg_name})",
                        "batch_per_gpu": B, "max_length": L, "joint_seq": 51 + L, "result_num": 224, "weights": "random init, seed 0",
                        "parallelism": f"dp{world} (batch-sharded, no collective in the forward)",
                        "l2": "4 distinct input batches rotated (154 MB) + 323 MB bf16 weights + >1 GB activations per step: working set >> 126 MB L2",

@@ -28,6 +28,8 @@ typedef struct CUstream_st* mvlt_stream_t; /* == cudaStream_t */
 #define MVLT_ACT_NONE 0
 #define MVLT_ACT_GELU 1 /* exact erf GELU (nn.GELU default), vfe.py:126, HF modeling_bert.py:336 */
 #define MVLT_ACT_TANH 2 /* BertPooler, HF modeling_bert.py:466 */
+#define MVLT_ACT_RELU 3 /* applied AFTER the residual add: torchvision resnet.py Bottleneck.forward (out += identity; relu) */
+#define MVLT_ACT_RELU_GELU 4 /* last bottleneck of the trunk: ReLU, then the nn.GELU of model.py:232-235 */
 
 /* One-time setup (driver entry points, opt-in shared memory sizes).  Call once per process after the CUDA
  * context exists and before any stream capture.  Also reports the library ABI version. */
@@ -37,11 +39,37 @@ int mvlt_abi_version(void);
 /* C[M,N] = act(A[M,K] . W[N,K]^T + bias) + residual — tcgen05/TMEM/TMA, bf16 operands, fp32 accumulate.
  * Replaces nn.Linear at vfe.py:231 (qkv), :252 (proj), :136/:139 (fc1/fc2), :443 (reduction, bias=NULL) and
  * HF modeling_bert.py:179-181 (Q|K|V packed as one [2304,768] weight), :295, :338, :352, :463, :476.
- * A,W bf16; C fp32|bf16 (out_dtype); bias fp32 or NULL; residual fp32|bf16 (res_dtype) or NULL.
- * K % 16 == 0, lda/ldw % 8 == 0.  block_n = 0 picks the tile width. */
+ * A,W bf16; C fp32|bf16 (out_dtype); bias fp32 or NULL; residual (or NULL) of C's dtype: fp32 C takes the fp32 residual
+ * stream (residual == C accumulates in place at the L2), bf16 C a bf16 residual (act NONE / RELU / RELU_GELU).
+ * MVLT_ACT_RELU / RELU_GELU need a bf16 C.  K % 16 == 0, lda/ldw % 8 == 0.  block_n = 0 picks the tile width. */
 int mvlt_gemm_bf16_tc(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc,
                       const float* bias, const void* residual, long long ldres, int res_dtype, int M, int N, int K,
                       int act, int out_dtype, int block_n, mvlt_stream_t stream);
+
+/* Conv2d over an NHWC bf16 activation as an implicit GEMM on the same tcgen05 kernel: the A operand is fetched by
+ * im2col-mode TMA (64 channels x 128 output pixels per filter tap and load; padding arrives as zeros), nothing is
+ * materialised.  out[B*Ho*Wo, N] (bf16, row stride ldc) = act(patches(x) . w^T + bias (+ residual)); w bf16 [N, R*S*C]
+ * packed TAP-MAJOR (k = (ky*S + kx)*C + c) with the eval-mode BatchNorm scale folded in, bias fp32 = the folded shift,
+ * residual bf16 [B*Ho*Wo, N] or NULL.  C % 64 == 0.  Replaces the nn.Conv2d + BatchNorm2d (+ ReLU, + identity) call
+ * sites of torchvision resnet.py Bottleneck.forward as used by vfe.py:7-24 / :27-44: conv2 (3x3, stride 1|2, pad 1) and
+ * the stride-2 1x1 downsample; stride-1 1x1 convolutions are plain mvlt_gemm_bf16_tc calls on the NHWC matrix. */
+int mvlt_conv2d_nhwc_bf16_tc(const void* x, int B, int H, int W, int C, const void* w, long long ldw, void* out,
+                             long long ldc, const float* bias, const void* residual, long long ldres, int N, int R, int S,
+                             int stride, int pad, int act, int block_n, mvlt_stream_t stream);
+
+/* Explicit tap-major patch matrix out[B*Ho*Wo, R*S*C] (row stride ld_out) of an NHWC activation (dtype fp32|bf16): the A
+ * operand of the fp32 parity-mode convolutions (mvlt_gemm_f32_simt); the bf16 path uses mvlt_conv2d_nhwc_bf16_tc. */
+int mvlt_im2col_nhwc(const void* x, int dtype, void* out, long long ld_out, int B, int H, int W, int C, int R, int S,
+                     int stride, int pad, mvlt_stream_t stream);
+
+/* Patch matrix of the ResNet stem (conv1 7x7/2 pad 3 on the 3-channel NCHW fp32 image, vfe.py:15 / resnet.py conv1):
+ * out[B*Ho*Wo, kpad] (out_dtype), k = (c*R + ky)*S + kx = conv1.weight.view(64, -1) order, columns >= Cin*R*S zero. */
+int mvlt_stem_im2col_nchw(const float* img, void* out, int out_dtype, long long ld_out, int B, int Cin, int H, int W, int R,
+                          int S, int stride, int pad, int kpad, mvlt_stream_t stream);
+
+/* nn.MaxPool2d(k, stride, pad) on NHWC (vfe.py:18: MaxPool2d(3, 2, 1) after the stem); dtype fp32|bf16. */
+int mvlt_maxpool_nhwc(const void* x, void* out, int dtype, int B, int H, int W, int C, int k, int stride, int pad,
+                      mvlt_stream_t stream);
 
 /* Fused MLP half of a Swin block, in place on the fp32 residual stream:  x += fc2(GELU(fc1(LayerNorm(x)))).
  * One tcgen05 kernel per call: LayerNorm in the prologue (fp32 statistics), the [128, 4C] hidden tile stays in shared
@@ -52,7 +80,8 @@ int mvlt_swin_mlp_fused(float* x, long long ldx, const float* gamma, const float
                         const float* b1, const void* w2, const float* b2, long long M, int C, int hidden,
                         mvlt_stream_t stream);
 
-/* Same contract as mvlt_gemm_bf16_tc in fp32 on the CUDA cores (parity mode, 1e-4 vs the reference). */
+/* Same contract as mvlt_gemm_bf16_tc in fp32 on the CUDA cores (parity mode, 1e-4 vs the reference); all five
+ * activation codes, fp32 residual. */
 int mvlt_gemm_f32_simt(const float* A, long long lda, const float* W, long long ldw, float* C, long long ldc,
                        const float* bias, const float* residual, long long ldres, int M, int N, int K, int act,
                        mvlt_stream_t stream);

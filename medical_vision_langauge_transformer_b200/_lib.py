@@ -18,6 +18,10 @@ PROTOTYPES = {
     "mvlt_init": [],
     "mvlt_abi_version": [],
     "mvlt_gemm_bf16_tc": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mvlt_conv2d_nhwc_bf16_tc": [_vp, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mvlt_im2col_nhwc": [_vp, _i, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mvlt_stem_im2col_nchw": [_vp, _vp, _i, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mvlt_maxpool_nhwc": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mvlt_swin_mlp_fused": [_vp, _ll, _vp, _vp, _f, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp],
     "mvlt_gemm_f32_simt": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
     "mvlt_layernorm_rows": [_vp, _i, _ll, _vp, _i, _ll, _vp, _vp, _ll, _i, _f, _i, _vp, _ll, _vp],

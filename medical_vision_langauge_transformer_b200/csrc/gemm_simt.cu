@@ -60,6 +60,10 @@ gemm_simt_kernel(const float* __restrict__ A, long long lda, const float* __rest
       if (act == 1) v = gelu_erf(v);
       else if (act == 2) v = tanhf(v);
       if (res) v += res[(long long)m * ldres + n];
+      if (act >= 3) {  // ResNet epilogues, applied after the residual add: 3 ReLU, 4 ReLU then erf-GELU
+        v = fmaxf(v, 0.f);
+        if (act == 4) v = gelu_erf(v);
+      }
       C[(long long)m * ldc + n] = v;
     }
   }

@@ -55,12 +55,13 @@ template <bool OUT_BF16, int RES, bool DEEP> struct Plan {
   // bf16 outputs (qkv, fc1/FFN-in + GELU): the per-chunk chain tcgen05.ld -> bias -> GELU -> pack -> st.shared -> fence ->
   // TMA store is latency-bound with two warps per scheduler (measured 1900 cycles per 32x32 chunk for ~300 issued
   // instructions, tools/gemm_trace.py) and those call sites are epilogue-bound: 16 warps = four per scheduler.
+  // bf16 output + bf16 residual (the conv3 + identity + ReLU epilogue of a ResNet bottleneck): 16 warps, two 2 KB buffers
   static constexpr int EPI_WARPS = RES == 2 ? (DEEP ? 8 : 16) : (DEEP ? 4 : (OUT_BF16 ? 16 : 8));
   static constexpr int THREADS = (4 + EPI_WARPS) * 32;       // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare
   static constexpr int EPI_PARTS = EPI_WARPS / 4;            // warps per TMEM lane quarter
   // staging buffers per warp: the residual variant prefetches chunk k+1 while k-1 still drains (3; DEEP: 2); with four
   // warps per scheduler a single buffer is enough — its previous store drains during the next chunk's tcgen05.ld + math
-  static constexpr int NBUF = RES == 1 ? (DEEP ? 2 : 3) : ((OUT_BF16 || RES == 2) ? 1 : 2);
+  static constexpr int NBUF = RES == 1 ? ((DEEP || OUT_BF16) ? 2 : 3) : ((OUT_BF16 || RES == 2) ? 1 : 2);
   static constexpr int BUF_BYTES = OUT_BF16 ? 2048 : 4096;
   static constexpr int STAGING_BYTES = EPI_WARPS * NBUF * BUF_BYTES;
   static constexpr int EPI_BYTES = STAGING_BYTES + EPI_WARPS * 128;   // + one 32-float bias slot per warp
@@ -79,6 +80,10 @@ struct GemmParams {
   int M, N, K;
   int block_n;
   int tiles_m, tiles_n;
+  // implicit-GEMM convolution (conv_cpb > 0): tmap_a is an im2col-mode tensor map over the NHWC input, GEMM row m is the
+  // output pixel (n, p, q) = unflatten(m; Ho*Wo, Wo) and k-block kb covers tap kb / conv_cpb = (ky, kx), channels
+  // 64 * (kb % conv_cpb) .. +64 (the weight is packed tap-major: [N, R*S*C])
+  int conv_cpb, conv_s, conv_wo, conv_howo, conv_stride, conv_pad;
   unsigned long long* trace;  // debug: clock64 stamps of CTA 0 (tools/gemm_trace.py); nullptr in production
 };
 static unsigned long long* g_gemm_trace = nullptr;
@@ -110,6 +115,18 @@ __device__ __forceinline__ void tma_load_cg2(void* smem_dst, const void* tmap, u
       ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
 }
+// im2col-mode TMA load (NHWC activation, rank-4 map {C, W, H, N}): 128 output pixels x 64 channels starting at the pixel
+// whose filter window has its corner at (w, h) in image n, shifted by the filter tap (off_w, off_h); out-of-image taps
+// and pixels beyond the last image arrive as zeros.  Same barrier convention as tma_load_cg2.
+__device__ __forceinline__ void tma_load_im2col_cg2(void* smem_dst, const void* tmap, uint64_t* bar, int c, int w, int h,
+                                                    int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
+        "h"(off_h)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -125,12 +142,16 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-// ACT: 0 none, 1 erf-GELU, 2 tanh.  OUT_BF16: C is bf16 (else fp32).  RES: see Plan (fp32 C only).
+// ACT: 0 none, 1 erf-GELU, 2 tanh, 3 ReLU, 4 ReLU then erf-GELU.  ACT 3/4 are the ResNet epilogues: applied LAST, after the
+// residual add (torchvision resnet.py Bottleneck.forward: out += identity; out = relu(out)), bf16 outputs only.
+// OUT_BF16: C is bf16 (else fp32).  RES: see Plan; fp32 C takes an fp32 residual (modes 1, 2), bf16 C a bf16 residual (mode 1).
 template <int ACT, bool OUT_BF16, int RES, bool DEEP>
 __global__ void __launch_bounds__((Plan<OUT_BF16, RES, DEEP>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, GemmParams p) {
-  static_assert(!(RES != 0 && OUT_BF16), "residual epilogue is fp32-in/fp32-out");
+  static_assert(!(RES == 2 && OUT_BF16), "reduce-add epilogue is fp32");
+  static_assert(ACT < 3 || OUT_BF16, "ReLU epilogues are bf16-out");
+  constexpr uint32_t RES_CHUNK_BYTES = 32 * 32 * (OUT_BF16 ? 2 : 4);
   using P = Plan<OUT_BF16, RES, DEEP>;
   constexpr int STAGES = P::STAGES, EPI_NBUF = P::NBUF, EPI_BUF_BYTES = P::BUF_BYTES, RING_BYTES = P::RING_BYTES;
   constexpr int EPI_BYTES = P::EPI_BYTES, NUM_BARS = P::NUM_BARS, NUM_EPI_WARPS = P::EPI_WARPS, EPI_PARTS = P::EPI_PARTS;
@@ -200,15 +221,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int tile = group; tile < num_tiles; tile += num_groups) {
       const int m0 = (tile / p.tiles_n) * (BM * CG) + rank * BM;
       const int n0 = (tile % p.tiles_n) * p.block_n + rank * b_rows;
+      // convolution: corner of the filter window of the CTA's first output pixel
+      int cw = 0, ch = 0, cn = 0;
+      if (p.conv_cpb > 0) {
+        cn = m0 / p.conv_howo;
+        const int rem = m0 - cn * p.conv_howo;
+        const int op = rem / p.conv_wo;
+        cw = (rem - op * p.conv_wo) * p.conv_stride - p.conv_pad;
+        ch = op * p.conv_stride - p.conv_pad;
+      }
+      int tap = 0, cb = 0;  // filter tap and 64-channel block of k-block kb (convolution)
       for (int kb = 0; kb < num_kb; ++kb, ++kc) {
         const uint32_t s = kc % STAGES, ph = (kc / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-          tma_load_cg2(smem_a + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BK, m0);
+          if (p.conv_cpb > 0) {
+            const int ky = tap / p.conv_s;
+            tma_load_im2col_cg2(smem_a + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], cb * BK, cw, ch, cn,
+                                (uint16_t)(tap - ky * p.conv_s), (uint16_t)ky);
+          } else {
+            tma_load_cg2(smem_a + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BK, m0);
+          }
           tma_load_cg2(smem_b + s * B_STAGE_BYTES, &tmap_b, &full_bar[s], kb * BK, n0);
         }
         __syncwarp();
+        if (++cb == p.conv_cpb) { cb = 0; ++tap; }
       }
     }
   } else if (warp == 1) {
@@ -297,7 +335,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (cur.ti < my_tiles) {
         const int m0 = cur.m0, n0 = cur.n0t + cur.c * 32;
         if (n0 < p.N && m0 < p.M && elect_one()) {
-          mbar_arrive_expect_tx(&rbar[0], 32 * 32 * 4);
+          mbar_arrive_expect_tx(&rbar[0], RES_CHUNK_BYTES);
           tma_load_2d(bufs, &tmap_r, &rbar[0], n0, m0);
         }
         __syncwarp();
@@ -341,7 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (has_next) {
           if (n1 < p.N && m1 < p.M) {
             const int nb = (k + 1) % EPI_NBUF;
-            mbar_arrive_expect_tx(&rbar[nb], 32 * 32 * 4);
+            mbar_arrive_expect_tx(&rbar[nb], RES_CHUNK_BYTES);
             tma_load_2d(bufs + nb * EPI_BUF_BYTES, &tmap_r, &rbar[nb], n1, m1);
           }
         }
@@ -380,6 +418,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         } else if (ACT == 2) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = make_float2(tanhf(v[i].x), tanhf(v[i].y));
+        } else if (ACT >= 3 && RES == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] = make_float2(fmaxf(v[i].x, 0.f), fmaxf(v[i].y, 0.f));
+            if (ACT == 4) v[i] = gelu_erf_pk2(v[i]);
+          }
         }
         if (tr_on) GEMM_STAMP(256 + 8 * k + 4);
         if (RES != 1) {  // buffer k % NBUF was last read by the store of step k - NBUF
@@ -387,6 +431,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           __syncwarp();
         }
         if (OUT_BF16) {
+          if (RES == 1) {  // bf16 residual chunk parked in this buffer by TMA: add in fp32, then the ReLU epilogues
+            uint4 t[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t[j] = *reinterpret_cast<const uint4*>(sb + row_base + (((uint32_t)j ^ swz) << 4));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              v[4 * j] = add2(v[4 * j], unpack_bf16x2(t[j].x));
+              v[4 * j + 1] = add2(v[4 * j + 1], unpack_bf16x2(t[j].y));
+              v[4 * j + 2] = add2(v[4 * j + 2], unpack_bf16x2(t[j].z));
+              v[4 * j + 3] = add2(v[4 * j + 3], unpack_bf16x2(t[j].w));
+            }
+            if (ACT >= 3) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                v[i] = make_float2(fmaxf(v[i].x, 0.f), fmaxf(v[i].y, 0.f));
+                if (ACT == 4) v[i] = gelu_erf_pk2(v[i]);
+              }
+            }
+          }
           // 8 bf16 (4 pairs) per 16 B slot
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -460,34 +523,47 @@ template <int ACT, bool OUT_BF16, int RES, bool DEEP> static Variant variant() {
   using P = Plan<OUT_BF16, RES, DEEP>;
   return Variant{gemm_tc_kernel<ACT, OUT_BF16, RES, DEEP>, P::SMEM_BYTES, P::THREADS};
 }
-// act 0..2; res 0..2; deep only with res != 0 and act == 0 (checked by the caller)
+// act 0..2: res 0..2 with fp32 C, res 0 with bf16 C; deep only with res != 0 and act == 0.  act 3/4 (ReLU epilogues): bf16 C
+// with res 0 or 1 (bf16 residual).  Returns a null kernel for combinations that are not compiled.
 static Variant pick_variant(int act, bool out_bf16, int res, bool deep) {
 #define MVLT_ACT(O, R, D) (act == 0 ? variant<0, O, R, D>() : act == 1 ? variant<1, O, R, D>() : variant<2, O, R, D>())
-  if (out_bf16) return MVLT_ACT(true, 0, false);
+  if (act >= 3) {
+    if (!out_bf16 || res == 2) return Variant{nullptr, 0, 0};
+    if (res == 1) return act == 3 ? variant<3, true, 1, false>() : variant<4, true, 1, false>();
+    return act == 3 ? variant<3, true, 0, false>() : variant<4, true, 0, false>();
+  }
+  if (out_bf16) return res == 0 ? MVLT_ACT(true, 0, false) : (res == 1 && act == 0 ? variant<0, true, 1, false>() : Variant{nullptr, 0, 0});
   if (res == 1) return deep ? variant<0, false, 1, true>() : MVLT_ACT(false, 1, false);
   if (res == 2) return deep ? variant<0, false, 2, true>() : MVLT_ACT(false, 2, false);
   return MVLT_ACT(false, 0, false);
 #undef MVLT_ACT
 }
 
+static PFN_cuTensorMapEncodeIm2col_v12000 g_encode_im2col = nullptr;
+
 static int gemm_tc_init() {
   if (g_encode) return MVLT_OK;
   void* fn = nullptr;
+  void* fn2 = nullptr;
   cudaDriverEntryPointQueryResult q;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
   if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return MVLT_ERR_DRIVER;
-  for (int act = 0; act < 3; ++act)
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn2, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn2) return MVLT_ERR_DRIVER;
+  for (int act = 0; act < 5; ++act)
     for (int o = 0; o < 2; ++o)
       for (int r = 0; r < 3; ++r)
         for (int d = 0; d < 2; ++d) {
-          if ((o && r) || (d && (!r || act != 0))) continue;
+          if (d && (!r || act != 0 || o)) continue;
           const Variant v = pick_variant(act, o != 0, r, d != 0);
+          if (!v.kernel) continue;
           e = cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem);
           if (e != cudaSuccess) return (int)e;
         }
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn2);
   g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   return MVLT_OK;
 }
@@ -541,21 +617,41 @@ extern "C" int mvlt_debug_gemm_trace(void* dev_buf) {
   return MVLT_OK;
 }
 
-extern "C" int mvlt_gemm_bf16_tc(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc,
-                                 const float* bias, const void* residual, long long ldres, int res_dtype, int M, int N,
-                                 int K, int act, int out_dtype, int block_n, cudaStream_t stream) {
+// Geometry of an implicit-GEMM convolution over an NHWC bf16 activation (nullptr = plain GEMM)
+struct ConvGeom {
+  int B, H, W, C, R, S, stride, pad, Ho, Wo;
+};
+
+// im2col-mode map over x[B, H, W, C] (bf16): 64 channels x 128 output pixels per load (CUTLASS fprop conventions:
+// lower corner = -pad, upper corner = pad - (filter - 1), traversal stride = convolution stride)
+static int make_tmap_im2col(CUtensorMap* map, const void* x, const ConvGeom& g) {
+  cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
+  cuuint64_t strides[3] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.W * g.C * 2, (cuuint64_t)g.H * g.W * g.C * 2};
+  int lower[2] = {-g.pad, -g.pad};
+  int upper[2] = {g.pad - (g.S - 1), g.pad - (g.R - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
+  CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, lower, upper,
+                               BK, BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MVLT_OK : MVLT_ERR_DRIVER;
+}
+
+static int gemm_launch(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc,
+                       const float* bias, const void* residual, long long ldres, int res_dtype, int M, int N, int K,
+                       int act, int out_dtype, int block_n, const ConvGeom* conv, cudaStream_t stream) {
   if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0) return MVLT_ERR_INVALID;
-  if (K % 16 != 0 || lda % 8 != 0 || ldw % 8 != 0) return MVLT_ERR_INVALID;  // TMA: 16 B aligned rows
+  if (K % 16 != 0 || ldw % 8 != 0 || (!conv && lda % 8 != 0)) return MVLT_ERR_INVALID;  // TMA: 16 B aligned rows
   if (((uintptr_t)A & 15) || ((uintptr_t)W & 15) || ((uintptr_t)C & 15)) return MVLT_ERR_INVALID;
-  if (act < 0 || act > 2 || (out_dtype != MVLT_F32 && out_dtype != MVLT_BF16)) return MVLT_ERR_INVALID;
+  if (act < 0 || act > 4 || (out_dtype != MVLT_F32 && out_dtype != MVLT_BF16)) return MVLT_ERR_INVALID;
   const bool out_bf16 = out_dtype == MVLT_BF16;
   if (ldc % (out_bf16 ? 8 : 4) != 0) return MVLT_ERR_INVALID;                // TMA store: 16 B aligned rows
   if (bias && ((uintptr_t)bias & 15)) return MVLT_ERR_INVALID;
   const bool res = residual != nullptr;
   if (res) {
-    // the fused residual is the fp32 residual stream of the model (Swin proj/fc2 in place, BERT attention/FFN outputs)
-    if (res_dtype != MVLT_F32 || out_bf16) return MVLT_ERR_UNSUPPORTED;
-    if (ldres % 4 != 0 || ((uintptr_t)residual & 15)) return MVLT_ERR_INVALID;
+    // fp32 C: the fp32 residual stream of the model (Swin proj/fc2 in place, BERT attention/FFN outputs);
+    // bf16 C: the bf16 identity branch of a ResNet bottleneck
+    if (res_dtype != (out_bf16 ? MVLT_BF16 : MVLT_F32)) return MVLT_ERR_UNSUPPORTED;
+    if (ldres % (out_bf16 ? 8 : 4) != 0 || ((uintptr_t)residual & 15)) return MVLT_ERR_INVALID;
   }
   int rc = gemm_tc_init();
   if (rc != MVLT_OK) return rc;
@@ -563,16 +659,24 @@ extern "C" int mvlt_gemm_bf16_tc(const void* A, long long lda, const void* W, lo
   if (block_n <= 0) block_n = pick_block_n(M, N, K, groups);
   if (block_n % 32 != 0 || block_n > BN_MAX) return MVLT_ERR_INVALID;
 
+  const bool deep = res && act == 0 && K >= 1024 && !out_bf16;
+  // in place (C is the fp32 residual): reduce-add stores; anything else: TMA-prefetched residual chunks
+  const int res_mode = !res ? 0 : ((!out_bf16 && residual == C && ldres == ldc) ? 2 : 1);
+  const Variant var = pick_variant(act, out_bf16, res_mode, deep);
+  if (!var.kernel) return MVLT_ERR_UNSUPPORTED;
+
   CUtensorMap ta, tb, tc, tr;
   const CUtensorMapDataType cdt = out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const CUtensorMapSwizzle cswz = out_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
-  if ((rc = make_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, M, K, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B,
-                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != MVLT_OK) return rc;
+  if (conv) {
+    if ((rc = make_tmap_im2col(&ta, A, *conv)) != MVLT_OK) return rc;
+  } else if ((rc = make_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, M, K, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != MVLT_OK) return rc;
   if ((rc = make_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, N, K, ldw, BK, block_n / CG, CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != MVLT_OK) return rc;
   if ((rc = make_tmap(&tc, cdt, out_bf16 ? 2 : 4, C, M, N, ldc, 32, 32, cswz, CU_TENSOR_MAP_L2_PROMOTION_NONE)) != MVLT_OK) return rc;
   if (res) {
-    if ((rc = make_tmap(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, residual, M, N, ldres, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B,
+    if ((rc = make_tmap(&tr, cdt, out_bf16 ? 2 : 4, residual, M, N, ldres, 32, 32, cswz,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) != MVLT_OK) return rc;
   } else {
     tr = tc;
@@ -582,16 +686,17 @@ extern "C" int mvlt_gemm_bf16_tc(const void* A, long long lda, const void* W, lo
   p.bias = bias; p.M = M; p.N = N; p.K = K; p.block_n = block_n;
   p.tiles_m = (M + BM * CG - 1) / (BM * CG);
   p.tiles_n = (N + block_n - 1) / block_n;
+  p.conv_cpb = 0; p.conv_s = 1; p.conv_wo = 1; p.conv_howo = 1; p.conv_stride = 1; p.conv_pad = 0;
+  if (conv) {
+    p.conv_cpb = conv->C / BK; p.conv_s = conv->S; p.conv_wo = conv->Wo; p.conv_howo = conv->Ho * conv->Wo;
+    p.conv_stride = conv->stride; p.conv_pad = conv->pad;
+  }
   p.trace = g_gemm_trace;
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = CG * (tiles < groups ? tiles : groups);
 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  const bool deep = res && act == 0 && K >= 1024;
-  // in place (C is the residual): reduce-add stores; anything else: TMA-prefetched residual chunks
-  const int res_mode = !res ? 0 : ((residual == C && ldres == ldc) ? 2 : 1);
-  const Variant var = pick_variant(act, out_bf16, res_mode, deep);
   cfg.blockDim = dim3(var.threads);
   cfg.dynamicSmemBytes = var.smem;
   cfg.stream = stream;
@@ -606,4 +711,28 @@ extern "C" int mvlt_gemm_bf16_tc(const void* A, long long lda, const void* W, lo
   cfg.numAttrs = mvlt_pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, var.kernel, ta, tb, tc, tr, p);
   return e == cudaSuccess ? MVLT_OK : (int)e;
+}
+
+extern "C" int mvlt_gemm_bf16_tc(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc,
+                                 const float* bias, const void* residual, long long ldres, int res_dtype, int M, int N,
+                                 int K, int act, int out_dtype, int block_n, cudaStream_t stream) {
+  return gemm_launch(A, lda, W, ldw, C, ldc, bias, residual, ldres, res_dtype, M, N, K, act, out_dtype, block_n, nullptr,
+                     stream);
+}
+
+extern "C" int mvlt_conv2d_nhwc_bf16_tc(const void* x, int B, int H, int W, int C, const void* w, long long ldw, void* out,
+                                        long long ldc, const float* bias, const void* residual, long long ldres, int N,
+                                        int R, int S, int stride, int pad, int act, int block_n, cudaStream_t stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || R <= 0 || S <= 0 || stride <= 0 || stride > 8 || pad < 0) return MVLT_ERR_INVALID;
+  if (C % BK != 0) return MVLT_ERR_UNSUPPORTED;                    // one k-block = 64 channels of one filter tap
+  if (pad > 127 || R - 1 - pad > 128 || S - 1 - pad > 128) return MVLT_ERR_UNSUPPORTED;  // im2col corner range (rank 4)
+  ConvGeom g;
+  g.B = B; g.H = H; g.W = W; g.C = C; g.R = R; g.S = S; g.stride = stride; g.pad = pad;
+  g.Ho = (H + 2 * pad - R) / stride + 1;
+  g.Wo = (W + 2 * pad - S) / stride + 1;
+  if (g.Ho <= 0 || g.Wo <= 0) return MVLT_ERR_INVALID;
+  const long long M = (long long)B * g.Ho * g.Wo;
+  if (M > 0x7fffffffLL) return MVLT_ERR_UNSUPPORTED;
+  return gemm_launch(x, 0, w, ldw, out, ldc, bias, residual, ldres, MVLT_BF16, (int)M, N, R * S * C, act, MVLT_BF16, block_n, &g,
+                     stream);
 }

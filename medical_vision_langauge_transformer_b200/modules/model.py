@@ -7,7 +7,7 @@ directories and whole-model pickles — load unchanged.  Weights keep PyTorch-de
 the reference, where `init_weights()` is never called (model.py:365).
 
 Out of scope here: the KV-cache decode branch of `get_embedding` (model.py:82-108) and
-`MVLBertForImageCaption`; the ResNet/ViT/linear backbones of `Conv_layer` (model.py:195-203,227-228).
+`MVLBertForImageCaption`; the ViT/linear backbones of `Conv_layer` (model.py:200-201,227-228).
 """
 from __future__ import annotations
 
@@ -19,7 +19,8 @@ from transformers import PreTrainedModel
 
 from .. import ops
 from .config import MVLBertConfig
-from .visual_feature_extractor import SwinTransformer, act_dtype, default_precision
+from .visual_feature_extractor import (SwinTransformer, act_dtype, default_precision, resnet50_without_poolfc,
+                                       resnet101_without_fc)
 
 # Swin-S, the only backbone config the reference ships enabled (modules/swin_small_patch4_window7_224.yaml:1-8 on top
 # of the defaults in swin_transformer_config.py); `Conv_layer(config, swin_kwargs=...)` overrides it.
@@ -237,29 +238,49 @@ class MVLBert(_PackedMixin, nn.Module):
 
 # ------------------------------------------------------------------------------------------------ Conv_layer
 class Conv_layer(nn.Module):
-    """model.py:186-266, Swin branch: Sequential(SwinTransformer, GELU) -> [B, 49, 768].  The final LayerNorm and the
-    GELU run as one kernel; the feature is returned in fp32 (as in the reference) in both precision modes."""
+    """model.py:186-266: Sequential(backbone, GELU) -> [B, 49, 768], returned in fp32 (as in the reference) in both
+    precision modes.  Swin branch: the final LayerNorm and the GELU run as one kernel.  ResNet-101 / ResNet-50 branch
+    (model.py:195-201): the GELU is the epilogue of the last bottleneck's GEMM, then `[B, 2048, 7, 7] -> [B, 49, 2048]`
+    (a no-op for NHWC activations) and `resnet_fc` (model.py:236, :263-264)."""
 
     def __init__(self, config, swin_kwargs=None, precision=None):
         super().__init__()
         self.config = config
         self.hidden_size = config.hidden_size if config is not None else 768
         kind = str(config.conv).lower()
-        if kind != "swintransformer":
-            if kind in ("resnet101", "resnet50", "linear", "vit", "visiontransformer"):
-                raise NotImplementedError(f"config.conv={config.conv!r}: only the Swin backbone is on the accelerated path "
-                                          "(ResNet-101 is the next row, SURVEY.md §8f-1)")
+        if str(config.conv) == "resnet101":
+            backbone = resnet101_without_fc(precision=precision)     # reference: ImageNet weights by URL (no network here)
+        elif str(config.conv) == "resnet50":
+            backbone = resnet50_without_poolfc(precision=precision)
+        elif kind == "swintransformer":
+            kw = dict(SWIN_SMALL)
+            kw.update(swin_kwargs or {})
+            backbone = SwinTransformer(precision=precision, **kw)
+        elif kind in ("linear", "vit", "visiontransformer"):
+            raise NotImplementedError(f"config.conv={config.conv!r}: only the Swin and ResNet backbones are on the accelerated path")
+        else:
             raise NotImplementedError("no such config.conv")
-        kw = dict(SWIN_SMALL)
-        kw.update(swin_kwargs or {})
-        self.conv = nn.Sequential(SwinTransformer(precision=precision, **kw), nn.GELU())
+        self.conv = nn.Sequential(backbone, nn.GELU())
         self.resnet_fc = nn.Linear(2048, config.hidden_size)     # unused on the Swin branch; kept for state_dict parity
+        self._fc_pk = None
+
+    def _fc_packed(self, precision):
+        w, b = self.resnet_fc.weight, self.resnet_fc.bias
+        key = (precision, w.device, w._version + b._version, id(w))
+        if self._fc_pk is None or self._fc_pk[0] != key:
+            self._fc_pk = (key, w.detach().to(act_dtype(precision)).contiguous(), b.detach().float().contiguous())
+        return self._fc_pk[1], self._fc_pk[2]
 
     def forward(self, v):
         if torch.is_tensor(v) and v.dim() == 5:
             raise NotImplementedError("5-D two-image IU-Xray input (model.py:240-253) is outside the accelerated path")
-        swin = self.conv[0]
-        return swin.forward_features(v, final_gelu=True, out_dtype=torch.float32)
+        backbone = self.conv[0]
+        if isinstance(backbone, SwinTransformer):
+            return backbone.forward_features(v, final_gelu=True, out_dtype=torch.float32)
+        a, H, W = backbone.forward_features(v, final_gelu=True)      # [B*49, 2048], GELU applied
+        fw, fb = self._fc_packed(backbone.precision)
+        feat = ops.linear(a, fw, fb, out_dtype=torch.float32)        # model.py:263-264 (channel == 2048)
+        return feat.view(v.shape[0], H * W, -1)
 
 
 # ------------------------------------------------------------------------------------------------ task models

@@ -288,3 +288,174 @@ class SwinTransformer(nn.Module):
 
     def forward(self, x):
         return self.forward_features(x)
+
+
+# ====================================================================================================================
+# ResNet backbones (vfe.py:7-44): torchvision ResNet-101 / ResNet-50 without pooling and fc, Bottleneck blocks.
+# ====================================================================================================================
+class Bottleneck(nn.Module):
+    """torchvision resnet.py Bottleneck parameter holder (v1.5: the stride sits on conv2): conv1 1x1 -> bn1 -> relu ->
+    conv2 3x3/stride -> bn2 -> relu -> conv3 1x1 -> bn3 -> (+ identity | downsample(x)) -> relu."""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, kernel_size=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * self.expansion, kernel_size=1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * self.expansion)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stride = stride
+
+
+def _fold_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d):
+    """Eval-mode BatchNorm2d folded into the convolution: y = conv(x; w * s) + (beta - mean * s), s = gamma / sqrt(var + eps).
+    -> (weight [N, R*S*C] tap-major fp32, bias [N] fp32)."""
+    s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    w = conv.weight.detach().float() * s[:, None, None, None]
+    b = bn.bias.detach().float() - bn.running_mean.detach().float() * s
+    if conv.bias is not None:
+        b = b + conv.bias.detach().float() * s
+    return w, b.contiguous()
+
+
+class ResNetWithoutFC(nn.Module):
+    """Module tree / state_dict keys of torchvision.models.ResNet(Bottleneck, layers, num_classes=1000) as subclassed by
+    vfe.py:7-24 (`resnet101_without_fc`) and :27-44 (`resnet50_without_poolfc`): `forward(x)` stops after layer4 and returns
+    [B, 2048, 7, 7].  `avgpool` / `fc` are constructed (their keys are in reference checkpoints) and never applied.
+    Initialisation as torchvision: kaiming-normal (fan_out, relu) convolutions, unit BatchNorm.  Eval-mode BatchNorm only
+    (running statistics folded into the GEMM weights): this is the forward path; `train()` statistics are out of scope.
+
+    Arithmetic: activations are NHWC matrices [B*H*W, C] (bf16 in bf16 mode); the stem is a patch-matrix kernel + GEMM,
+    1x1 convolutions are tcgen05 GEMMs on the matrix as is, 3x3 and strided convolutions are the same GEMM kernel with its
+    A operand fetched by im2col-mode TMA, BatchNorm + ReLU + the identity add live in the GEMM epilogue."""
+
+    def __init__(self, layers, pretrained=False, progress=False, precision=None, num_classes=1000):
+        super().__init__()
+        if pretrained:
+            raise RuntimeError("no network: torchvision ImageNet weights cannot be downloaded here; load a state_dict "
+                               "(the key layout is torchvision's) after construction")
+        self.inplanes = 64
+        self.precision = precision or default_precision()
+        self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        self.layer1 = self._make_layer(64, layers[0])
+        self.layer2 = self._make_layer(128, layers[1], stride=2)
+        self.layer3 = self._make_layer(256, layers[2], stride=2)
+        self.layer4 = self._make_layer(512, layers[3], stride=2)
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self.fc = nn.Linear(512 * Bottleneck.expansion, num_classes)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+        self.num_features = 512 * Bottleneck.expansion
+        self._packed = None
+        self._packed_key = None
+        self.taps = None
+
+    def _make_layer(self, planes, blocks, stride=1):
+        downsample = None
+        if stride != 1 or self.inplanes != planes * Bottleneck.expansion:
+            downsample = nn.Sequential(nn.Conv2d(self.inplanes, planes * Bottleneck.expansion, kernel_size=1, stride=stride, bias=False),
+                                       nn.BatchNorm2d(planes * Bottleneck.expansion))
+        layers = [Bottleneck(self.inplanes, planes, stride, downsample)]
+        self.inplanes = planes * Bottleneck.expansion
+        layers += [Bottleneck(self.inplanes, planes) for _ in range(1, blocks)]
+        return nn.Sequential(*layers)
+
+    # ---------------------------------------------------------------- packed weights
+    STEM_KPAD = 160   # 3*7*7 = 147 rounded up to the GEMM's K granule
+
+    def _fingerprint(self):
+        ts = list(self.parameters()) + [b for n, b in self.named_buffers() if "running" in n]
+        return (self.precision, self.conv1.weight.device, sum(t._version for t in ts), id(self.conv1.weight))
+
+    def packed(self):
+        key = self._fingerprint()
+        if self._packed is None or self._packed_key != key:
+            wd = act_dtype(self.precision)
+
+            def conv_bn(conv, bn):
+                w, b = _fold_bn(conv, bn)
+                n = w.shape[0]
+                return w.permute(0, 2, 3, 1).reshape(n, -1).to(wd).contiguous(), b     # tap-major [N, R*S*C]
+
+            w, b = _fold_bn(self.conv1, self.bn1)
+            stem = torch.zeros(w.shape[0], self.STEM_KPAD, device=w.device, dtype=torch.float32)
+            stem[:, :w[0].numel()] = w.reshape(w.shape[0], -1)                       # (c, ky, kx) order, zero padded
+            pk = {"stem_w": stem.to(wd).contiguous(), "stem_b": b, "blocks": []}
+            for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+                for blk in layer:
+                    d = dict(stride=blk.stride)
+                    d["w1"], d["b1"] = conv_bn(blk.conv1, blk.bn1)
+                    d["w2"], d["b2"] = conv_bn(blk.conv2, blk.bn2)
+                    d["w3"], d["b3"] = conv_bn(blk.conv3, blk.bn3)
+                    if blk.downsample is not None:
+                        d["wd"], d["bd"] = conv_bn(blk.downsample[0], blk.downsample[1])
+                    pk["blocks"].append(d)
+            self._packed, self._packed_key = pk, key
+        return self._packed
+
+    # ---------------------------------------------------------------- forward
+    def forward_features(self, x, final_gelu: bool = False):
+        """-> NHWC matrix [B*Ho*Wo, 2048] in the activation dtype (+ the nn.GELU of model.py:232-235 when final_gelu)."""
+        if self.training:
+            raise NotImplementedError("train-mode BatchNorm (batch statistics) is outside the accelerated forward path; "
+                                      "call model.eval()")
+        if not x.is_cuda:
+            raise RuntimeError("mvlt_b200 ResNet runs on CUDA (sm_100a) only; move the model and inputs to the GPU")
+        B, Cin, H, W = x.shape
+        assert Cin == 3, "ResNet stem expects 3 input channels"
+        pk = self.packed()
+        adt = act_dtype(self.precision)
+        x = x.contiguous().float()
+        a = ops.stem_im2col(x, 7, 7, 2, 3, self.STEM_KPAD, adt)
+        a = ops.linear(a, pk["stem_w"], pk["stem_b"], act=ops.ACT_RELU)
+        H, W = ops.conv_out_hw(H, W, 7, 7, 2, 3)
+        a = ops.maxpool_nhwc(a, B, H, W, 3, 2, 1)
+        H, W = ops.conv_out_hw(H, W, 3, 3, 2, 1)
+        taps = self.taps
+        if taps is not None:
+            taps["stem"] = a.float().view(B, H, W, -1).permute(0, 3, 1, 2).clone()
+        n_blocks = len(pk["blocks"])
+        bi = 0
+        for li, layer in enumerate((self.layer1, self.layer2, self.layer3, self.layer4)):
+            for _ in layer:
+                w = pk["blocks"][bi]
+                bi += 1
+                s = w["stride"]
+                h = ops.linear(a, w["w1"], w["b1"], act=ops.ACT_RELU)
+                h = ops.conv2d_nhwc(h, w["w2"], w["b2"], B, H, W, 3, 3, s, 1, act=ops.ACT_RELU)
+                idn = ops.conv2d_nhwc(a, w["wd"], w["bd"], B, H, W, 1, 1, s, 0) if "wd" in w else a
+                H, W = ops.conv_out_hw(H, W, 3, 3, s, 1)
+                last = final_gelu and bi == n_blocks
+                a = ops.linear(h, w["w3"], w["b3"], act=ops.ACT_RELU_GELU if last else ops.ACT_RELU, residual=idn)
+            if taps is not None and not (final_gelu and bi == n_blocks):   # layer4 of the fused-GELU call is not the raw output
+                taps[f"layer{li + 1}"] = a.float().view(B, H, W, -1).permute(0, 3, 1, 2).clone()
+        return a, H, W
+
+    def forward(self, x):
+        a, H, W = self.forward_features(x)
+        return a.float().view(x.shape[0], H, W, -1).permute(0, 3, 1, 2)
+
+
+class resnet101_without_fc(ResNetWithoutFC):
+    """vfe.py:7-24."""
+
+    def __init__(self, pretrained=False, progress=False, precision=None):
+        super().__init__([3, 4, 23, 3], pretrained, progress, precision)
+
+
+class resnet50_without_poolfc(ResNetWithoutFC):
+    """vfe.py:27-44."""
+
+    def __init__(self, pretrained=False, progress=False, precision=None):
+        super().__init__([3, 4, 6, 3], pretrained, progress, precision)

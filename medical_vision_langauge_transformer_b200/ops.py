@@ -9,7 +9,7 @@ import torch
 from . import _lib
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_GELU, ACT_TANH = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_TANH, ACT_RELU, ACT_RELU_GELU = 0, 1, 2, 3, 4
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
 
@@ -40,7 +40,8 @@ def _rows2d(t: torch.Tensor):
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
            out_dtype: Optional[torch.dtype] = None, block_n: int = 0) -> torch.Tensor:
-    """out = act(x @ w.T + bias) + residual.  bf16 x/w -> tcgen05 GEMM; fp32 x/w -> CUDA-core parity GEMM."""
+    """out = act(x @ w.T + bias) + residual (ACT_RELU / ACT_RELU_GELU: act applied after the residual add).
+    bf16 x/w -> tcgen05 GEMM; fp32 x/w -> CUDA-core parity GEMM."""
     lib = _lib.ensure_init()
     M, K, lda = _rows2d(x)
     N, Kw, ldw = _rows2d(w)
@@ -67,6 +68,70 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         rc = lib.mvlt_gemm_f32_simt(x.data_ptr(), lda, w.data_ptr(), ldw, out.data_ptr(), ldc, _ptr(bias), _ptr(residual),
                                     ldres, M, N, K, act, _stream())
         _lib.check(rc, f"mvlt_gemm_f32_simt(M={M},N={N},K={K})")
+    return out
+
+
+def conv_out_hw(H: int, W: int, R: int, S: int, stride: int, pad: int):
+    return (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+
+
+def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], B: int, H: int, W: int, R: int, S: int,
+                stride: int, pad: int, act: int = ACT_NONE, residual: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Conv2d (+ folded BatchNorm bias, + identity, + ReLU) over the NHWC activation x [B*H*W, C] -> [B*Ho*Wo, N].
+    w [N, R*S*C] tap-major (k = (ky*S + kx)*C + c).  bf16: implicit GEMM, A fetched by im2col-mode TMA inside the tcgen05
+    kernel; fp32 (parity mode): explicit patch matrix + CUDA-core GEMM."""
+    lib = _lib.ensure_init()
+    rows, C, ld = _rows2d(x)
+    assert rows == B * H * W and ld == C and x.is_contiguous(), "NHWC activation must be a dense [B*H*W, C] matrix"
+    N, K, ldw = _rows2d(w)
+    assert K == R * S * C and w.dtype == x.dtype
+    Ho, Wo = conv_out_hw(H, W, R, S, stride, pad)
+    M = B * Ho * Wo
+    if x.dtype != torch.bfloat16:
+        if R == S == 1 and stride == 1 and pad == 0:
+            return linear(x, w, bias, act=act, residual=residual, out=out)
+        patches = torch.empty((M, K), device=x.device, dtype=x.dtype)
+        rc = lib.mvlt_im2col_nhwc(x.data_ptr(), _code(x), patches.data_ptr(), K, B, H, W, C, R, S, stride, pad, _stream())
+        _lib.check(rc, "mvlt_im2col_nhwc")
+        return linear(patches, w, bias, act=act, residual=residual, out=out)
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
+    Mo, No, ldc = _rows2d(out)
+    assert (Mo, No) == (M, N) and out.dtype == torch.bfloat16
+    ldres = 0
+    if residual is not None:
+        Mr, Nr, ldres = _rows2d(residual)
+        assert (Mr, Nr) == (M, N) and residual.dtype == torch.bfloat16
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
+    rc = lib.mvlt_conv2d_nhwc_bf16_tc(x.data_ptr(), B, H, W, C, w.data_ptr(), ldw, out.data_ptr(), ldc, _ptr(bias),
+                                      _ptr(residual), ldres, N, R, S, stride, pad, act, 0, _stream())
+    _lib.check(rc, f"mvlt_conv2d_nhwc_bf16_tc(B={B},H={H},W={W},C={C},N={N},k={R}x{S},s={stride})")
+    return out
+
+
+def stem_im2col(img: torch.Tensor, R: int, S: int, stride: int, pad: int, kpad: int, out_dtype: torch.dtype) -> torch.Tensor:
+    """NCHW fp32 image -> patch matrix [B*Ho*Wo, kpad] (k = (c*R + ky)*S + kx, zero padded) for the ResNet stem conv."""
+    lib = _lib.ensure_init()
+    assert img.dtype == torch.float32 and img.is_contiguous() and img.dim() == 4
+    B, Cin, H, W = img.shape
+    Ho, Wo = conv_out_hw(H, W, R, S, stride, pad)
+    out = torch.empty((B * Ho * Wo, kpad), device=img.device, dtype=out_dtype)
+    rc = lib.mvlt_stem_im2col_nchw(img.data_ptr(), out.data_ptr(), _code(out), kpad, B, Cin, H, W, R, S, stride, pad, kpad,
+                                   _stream())
+    _lib.check(rc, "mvlt_stem_im2col_nchw")
+    return out
+
+
+def maxpool_nhwc(x: torch.Tensor, B: int, H: int, W: int, k: int, stride: int, pad: int) -> torch.Tensor:
+    lib = _lib.ensure_init()
+    rows, C, ld = _rows2d(x)
+    assert rows == B * H * W and ld == C and x.is_contiguous()
+    Ho, Wo = conv_out_hw(H, W, k, k, stride, pad)
+    out = torch.empty((B * Ho * Wo, C), device=x.device, dtype=x.dtype)
+    rc = lib.mvlt_maxpool_nhwc(x.data_ptr(), out.data_ptr(), _code(x), B, H, W, C, k, stride, pad, _stream())
+    _lib.check(rc, "mvlt_maxpool_nhwc")
     return out
 
 

@@ -16,12 +16,15 @@ Two weight flavours:
 from __future__ import annotations
 
 import math
+import re
 import zlib
 from typing import Dict, Mapping
 
 import torch
 
-_BUFFERS = ("relative_position_index", "attn_mask", "position_ids")
+_BUFFERS = ("relative_position_index", "attn_mask", "position_ids", "num_batches_tracked")
+_RESNET = re.compile(r"^conv\.conv\.0\.(conv1|bn1|layer[1-4]|fc)\.")      # torchvision ResNet keys under Conv_layer
+_BATCHNORM = re.compile(r"\.(bn\d|downsample\.1)\.(weight|bias|running_mean|running_var)$")
 
 
 def _gen(name: str, seed: int) -> torch.Generator:
@@ -35,6 +38,8 @@ def synth_tensor(name: str, shape, seed: int = 0, flavour: str = "stress") -> to
     shape = tuple(shape)
     randn = lambda s=1.0: torch.randn(shape, generator=g) * s
     leaf = name.rsplit(".", 1)[-1]
+    if _RESNET.match(name) and ".fc." not in name:
+        return _synth_resnet(name, shape, g, flavour)
     is_swin = name.startswith("conv.conv.0.")
     is_ln = any(t in name for t in ("norm", "LayerNorm")) and "downsample.reduction" not in name
     if is_ln:
@@ -61,6 +66,26 @@ def synth_tensor(name: str, shape, seed: int = 0, flavour: str = "stress") -> to
             bound *= 2.0
         return (torch.rand(shape, generator=g) * 2 - 1) * bound
     return randn(0.02)
+
+
+def _synth_resnet(name: str, shape, g: torch.Generator, flavour: str) -> torch.Tensor:
+    """ResNet trunk (vfe.py:7-44).  "init": torchvision's construction (kaiming-normal fan_out convolutions, unit BatchNorm,
+    fresh running statistics).  "stress": fan_in He convolutions and non-trivial BatchNorm parameters / running statistics;
+    the last BatchNorm of each bottleneck has a gain around 0.25 so 33 residual blocks stay O(10) instead of doubling the
+    variance per block (which only tests the exponent range)."""
+    leaf = name.rsplit(".", 1)[-1]
+    randn = lambda s=1.0: torch.randn(shape, generator=g) * s
+    if _BATCHNORM.search(name):
+        if flavour == "init":
+            return torch.ones(shape) if leaf in ("weight", "running_var") else torch.zeros(shape)
+        if leaf == "weight":
+            return (0.25 + randn(0.025)) if ".bn3." in name else (1.0 + randn(0.1))
+        if leaf == "running_var":
+            return 0.8 + 0.4 * torch.rand(shape, generator=g)
+        return randn(0.05)
+    assert leaf == "weight" and len(shape) == 4, name
+    n, c, r, s = shape
+    return randn(math.sqrt(2.0 / (n * r * s))) if flavour == "init" else randn(math.sqrt(2.0 / (c * r * s)))
 
 
 def synth_state_dict(shapes: Mapping[str, torch.Size], seed: int = 0, flavour: str = "stress") -> Dict[str, torch.Tensor]:

@@ -38,12 +38,18 @@ def attach_taps(model, taps: dict):
     """Forward hooks on the reference modules; names match oracle.mvlt_oracle taps."""
     hs = []
     swin = model.conv.conv[0]
-    hs.append(swin.patch_embed.register_forward_hook(lambda m, i, o: taps.__setitem__("patch_embed", o)))
-    for s, layer in enumerate(swin.layers):
-        for b in (0, 1):
-            hs.append(layer.blocks[b].register_forward_hook(
-                lambda m, i, o, k=f"s{s}b{b}": taps.__setitem__(k, o)))
-        hs.append(layer.register_forward_hook(lambda m, i, o, k=f"stage{s}": taps.__setitem__(k, o)))
+    if hasattr(swin, "layer1"):           # ResNet trunk (vfe.py:7-44): stem output after the max-pool, then each stage
+        hs.append(swin.maxpool.register_forward_hook(lambda m, i, o: taps.__setitem__("stem", o)))
+        for li in (1, 2, 3, 4):
+            hs.append(getattr(swin, f"layer{li}").register_forward_hook(
+                lambda m, i, o, k=f"layer{li}": taps.__setitem__(k, o)))
+    else:
+        hs.append(swin.patch_embed.register_forward_hook(lambda m, i, o: taps.__setitem__("patch_embed", o)))
+        for s, layer in enumerate(swin.layers):
+            for b in (0, 1):
+                hs.append(layer.blocks[b].register_forward_hook(
+                    lambda m, i, o, k=f"s{s}b{b}": taps.__setitem__(k, o)))
+            hs.append(layer.register_forward_hook(lambda m, i, o, k=f"stage{s}": taps.__setitem__(k, o)))
     hs.append(model.conv.register_forward_hook(lambda m, i, o: taps.__setitem__("image_feature", o)))
     enc = model.MVLBert.encoder
     hs.append(enc.register_forward_pre_hook(
@@ -55,8 +61,8 @@ def attach_taps(model, taps: dict):
     return hs
 
 
-def case_retrieval(flavour, img_scale, B=2, L=80):
-    m = build_reference_model("retrieval", max_length=L)
+def case_retrieval(flavour, img_scale, B=2, L=80, conv="swintransformer"):
+    m = build_reference_model("retrieval", max_length=L, conv=conv)
     synth.load_synth(m, 0, flavour)
     x, ids = synth.synth_images(B, 1, img_scale), synth.synth_token_ids(B, L, 1)
     taps = {}
@@ -65,7 +71,7 @@ def case_retrieval(flavour, img_scale, B=2, L=80):
         prob = m(x, ids)
         logits = m(x, ids, image_text_label=torch.zeros(B, dtype=torch.long))
     [h.remove() for h in hs]
-    return {"task": "retrieval", "flavour": flavour, "img_scale": img_scale, "B": B, "L": L, "weight_seed": 0,
+    return {"task": "retrieval", "flavour": flavour, "img_scale": img_scale, "B": B, "L": L, "weight_seed": 0, "conv": conv,
             "data_seed": 1, "prob": prob, "logits": logits, "taps": {k: probe(v, k) for k, v in taps.items()}}
 
 
@@ -121,17 +127,38 @@ def case_rank(N=6, L=80):
             "labels": labels}
 
 
+def write_state_dict_keys():
+    """tests/golden/state_dict_keys.json: key -> shape of the REAL reference's task models, in state_dict order."""
+    import json
+    out = {}
+    for task in ("vqa", "retrieval", "pretrain"):
+        out[task] = {k: list(v.shape) for k, v in build_reference_model(task).state_dict().items()}
+    for conv in ("resnet101", "resnet50"):
+        m = build_reference_model("retrieval", max_length=80, conv=conv)
+        out[f"retrieval_{conv}"] = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(GOLDEN_DIR, "state_dict_keys.json"), "w") as f:
+        json.dump(out, f)
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    if sys.argv[1:] == ["state_dict_keys"]:
+        return write_state_dict_keys()
     torch.set_num_threads(os.cpu_count())
     cases = {
-        "retrieval_stress": case_retrieval("stress", 1.0),
-        "retrieval_config1": case_retrieval("init", 0.02),       # BASELINE.json configs[0]
-        "vqa_stress": case_vqa(),
-        "pretrain_stress": case_pretrain(),
-        "rank6": case_rank(),
+        "retrieval_stress": lambda: case_retrieval("stress", 1.0),
+        "retrieval_config1": lambda: case_retrieval("init", 0.02),       # BASELINE.json configs[0]
+        "vqa_stress": case_vqa,
+        "pretrain_stress": case_pretrain,
+        "rank6": case_rank,
+        "retrieval_resnet101": lambda: case_retrieval("stress", 1.0, conv="resnet101"),   # BASELINE.json configs[4] backbone
+        "retrieval_resnet50": lambda: case_retrieval("stress", 1.0, conv="resnet50"),
     }
-    for name, c in cases.items():
+    only = sys.argv[1:]                         # `python -m oracle.make_golden NAME...` regenerates just those cases
+    for name, fn in cases.items():
+        if only and name not in only:
+            continue
+        c = fn()
         path = os.path.join(GOLDEN_DIR, name + ".pt")
         torch.save(c, path)
         print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")

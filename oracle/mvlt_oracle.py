@@ -145,8 +145,55 @@ def swin_forward(sd: SD, img: Tensor, prefix: str = "conv.conv.0.", cfg=SWIN_S, 
     return F.layer_norm(x, (C,), sd[prefix + "norm.weight"], sd[prefix + "norm.bias"], 1e-5)
 
 
+# ----------------------------------------------------------------------------------------------
+# ResNet backbones (third-party arithmetic: torchvision/models/resnet.py, reference pin torchvision>=0.12.0, README.md:5)
+# ----------------------------------------------------------------------------------------------
+RESNET_LAYERS = {"resnet101": (3, 4, 23, 3), "resnet50": (3, 4, 6, 3)}
+
+
+def _bn_eval(sd: SD, p: str, x: Tensor) -> Tensor:
+    """nn.BatchNorm2d in eval mode (running statistics, eps 1e-5)."""
+    return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"], False, 0.0, 1e-5)
+
+
+def bottleneck(sd: SD, p: str, x: Tensor, stride: int) -> Tensor:
+    """torchvision resnet.py Bottleneck.forward (v1.5: stride on conv2): 1x1 -> bn -> relu -> 3x3/stride -> bn -> relu ->
+    1x1 -> bn -> += identity (downsample = 1x1/stride conv + bn when present) -> relu."""
+    out = F.relu(_bn_eval(sd, p + "bn1.", F.conv2d(x, sd[p + "conv1.weight"])))
+    out = F.relu(_bn_eval(sd, p + "bn2.", F.conv2d(out, sd[p + "conv2.weight"], stride=stride, padding=1)))
+    out = _bn_eval(sd, p + "bn3.", F.conv2d(out, sd[p + "conv3.weight"]))
+    if p + "downsample.0.weight" in sd:
+        x = _bn_eval(sd, p + "downsample.1.", F.conv2d(x, sd[p + "downsample.0.weight"], stride=stride))
+    return F.relu(out + x)
+
+
+def resnet_forward(sd: SD, img: Tensor, prefix: str = "conv.conv.0.", layers=RESNET_LAYERS["resnet101"],
+                   taps: Optional[dict] = None) -> Tensor:
+    """vfe.py:14-24 `_forward_impl`: conv1 7x7/2 -> bn1 -> relu -> maxpool 3x3/2 -> layer1..4; no avgpool, no fc.
+    -> [B, 2048, 7, 7]"""
+    x = F.relu(_bn_eval(sd, prefix + "bn1.", F.conv2d(img, sd[prefix + "conv1.weight"], stride=2, padding=3)))
+    x = F.max_pool2d(x, 3, 2, 1)
+    if taps is not None:
+        taps["stem"] = x
+    for li, depth in enumerate(layers):
+        for b in range(depth):
+            x = bottleneck(sd, f"{prefix}layer{li + 1}.{b}.", x, 2 if (b == 0 and li > 0) else 1)
+        if taps is not None:
+            taps[f"layer{li + 1}"] = x
+    return x
+
+
 def conv_layer(sd: SD, img: Tensor, taps: Optional[dict] = None) -> Tensor:
-    """model.py:232-235,255-266 — Sequential(swin, GELU); 4-D branch; feature dim 768 so no resnet_fc."""
+    """model.py:232-235,255-266 — Sequential(backbone, GELU); 4-D branch.  Swin: feature dim 768 so no resnet_fc.
+    ResNet (keys `conv.conv.0.layer1...`): [B,2048,7,7] -> reshape/transpose [B,49,2048] (:258-261) -> resnet_fc (:263-264);
+    the depth is read off the state_dict (layer3 has 23 blocks for resnet101, 6 for resnet50)."""
+    if "conv.conv.0.layer1.0.conv1.weight" in sd:
+        layers = tuple(sum(1 for k in sd if k.startswith(f"conv.conv.0.layer{i}.") and k.endswith(".conv1.weight"))
+                       for i in (1, 2, 3, 4))
+        x = F.gelu(resnet_forward(sd, img, "conv.conv.0.", layers, taps))
+        B, C = x.shape[:2]
+        x = x.reshape(B, C, -1).transpose(1, 2)
+        return F.linear(x, sd["conv.resnet_fc.weight"], sd["conv.resnet_fc.bias"])
     return F.gelu(swin_forward(sd, img, "conv.conv.0.", taps=taps))
 
 
@@ -316,8 +363,32 @@ def recall_at(ranks, ks=(1, 5, 10)):
     return [sum(r < k for r in ranks) / len(ranks) for k in ks]
 
 
-def flops_per_pair(L: int = 80) -> float:
-    """Algorithmic FLOPs (MAC*2, unpadded) of one Swin-S + BERT-base pair — BASELINE.md §3."""
+def resnet_flops(layers=RESNET_LAYERS["resnet101"], img: int = 224) -> float:
+    """Algorithmic FLOPs (MAC*2) of the Bottleneck trunk (stem + layer1-4, no fc) per image — SURVEY.md §8d: 15.60 G for
+    ResNet-101 at 224^2."""
+    H = img // 2
+    f = 2.0 * H * H * 64 * 3 * 49
+    H //= 2
+    inpl = 64
+    for li, depth in enumerate(layers):
+        planes = 64 * 2 ** li
+        for b in range(depth):
+            stride = 2 if (b == 0 and li > 0) else 1
+            Ho = H // stride
+            f += 2.0 * H * H * inpl * planes + 2.0 * Ho * Ho * planes * planes * 9 + 2.0 * Ho * Ho * planes * planes * 4
+            if b == 0:
+                f += 2.0 * Ho * Ho * inpl * planes * 4
+            inpl, H = planes * 4, Ho
+    return f
+
+
+def flops_per_pair(L: int = 80, conv: str = "swintransformer") -> float:
+    """Algorithmic FLOPs (MAC*2, unpadded) of one Swin-S + BERT-base pair — BASELINE.md §3 (conv="resnet101"/"resnet50":
+    the Bottleneck trunk + resnet_fc instead of Swin-S)."""
+    if conv in RESNET_LAYERS:
+        S = 51 + L
+        bert = 12 * (2 * S * 768 * (3 * 768 + 768 + 2 * 3072) + 2 * 2 * 12 * S * S * 64)
+        return resnet_flops(RESNET_LAYERS[conv]) + 2 * 49 * 2048 * 768 + bert + 2 * 768 * 768 * 2
     swin = 0.0
     res = 56
     swin += 2 * 3136 * 48 * 96

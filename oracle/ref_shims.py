@@ -15,6 +15,7 @@ Shims (none touches the math):
   yacs.config.CfgNode  -> attr-dict with merge/clone/freeze                       (swin_transformer_config.py:14)
   transformers.BeamSearchScorer -> placeholder (only report generation uses it)   (model.py:7)
   torch.load           -> {'model': {}} for the absent Swin .pth (strict=False)   (model.py:222-225)
+  torchvision model_urls / load_state_dict_from_url -> offline random-init state_dict (ResNet variants)  (vfe.py:11)
 """
 from __future__ import annotations
 
@@ -179,13 +180,29 @@ def import_reference():
     return _ref_modules
 
 
-def make_reference_config(task: str, max_length: int = 80, result_num: int = 224, itm: bool = True):
+def _install_resnet_shim(ref_vfe):
+    """vfe.py:11 reads `torchvision.models.resnet.model_urls` (removed from torchvision >= 0.13) and downloads the ImageNet
+    weights; model.py:196-199 hard-codes PRETRAIN=True.  There is no network: hand back a random-init state_dict (the
+    caller overwrites every tensor with synthetic values anyway)."""
+    import torchvision
+    if not hasattr(torchvision.models.resnet, "model_urls"):
+        torchvision.models.resnet.model_urls = {"resnet101": "offline://resnet101", "resnet50": "offline://resnet50"}
+
+    def _offline_state_dict(url, *a, **kw):
+        name = url.rsplit("/", 1)[-1]
+        return getattr(torchvision.models, name)(weights=None).state_dict()
+
+    ref_vfe.load_state_dict_from_url = _offline_state_dict
+
+
+def make_reference_config(task: str, max_length: int = 80, result_num: int = 224, itm: bool = True,
+                          conv: str = "swintransformer"):
     """Config objects as the run_*.py scripts would build them, without network."""
     _, ref_config, _ = import_reference()
     cls = {"vqa": ref_config.MVLBertConfigforVQA, "retrieval": ref_config.MVLBertRetrieval,
            "pretrain": ref_config.MVLBertPretrainConfig}[task]
     cfg = cls()
-    cfg.conv = "swintransformer"
+    cfg.conv = conv
     cfg.vocab_size = 30522
     cfg.cls_token_id, cfg.sep_token_id, cfg.eos_token_id, cfg.mask_token_id = 101, 102, 104, 103
     cfg.max_length = max_length
@@ -198,8 +215,10 @@ def make_reference_config(task: str, max_length: int = 80, result_num: int = 224
 def build_reference_model(task: str, seed: int = 0, **cfg_kw):
     """The real reference task model (eval mode), random init under torch.manual_seed(seed)."""
     import torch
-    ref_model, _, _ = import_reference()
+    ref_model, _, ref_vfe = import_reference()
     cfg = make_reference_config(task, **cfg_kw)
+    if cfg.conv.startswith("resnet"):
+        _install_resnet_shim(ref_vfe)
     cls = {"vqa": ref_model.MVLBertForVQA, "retrieval": ref_model.MVLBertForRetrieval,
            "pretrain": ref_model.MVLBertForPretraining}[task]
     with _reference_cwd():

@@ -46,6 +46,30 @@ def test_state_dict_layout_matches_reference(task):
     assert all(list(sd[k].shape) == ref[k] for k in ref)
 
 
+@pytest.mark.parametrize("conv", ["resnet101", "resnet50"])
+def test_resnet_state_dict_layout_matches_reference(conv):
+    """torchvision ResNet key layout under `conv.conv.0.` (incl. the never-applied fc and the BatchNorm buffers) + resnet_fc."""
+    from medical_vision_langauge_transformer_b200.modules import config as C, model as M
+    ref = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))[f"retrieval_{conv}"]
+    sd = M.MVLBertForRetrieval(C.offline_config("retrieval", conv=conv)).state_dict()
+    assert list(sd) == list(ref)
+    assert all(list(sd[k].shape) == ref[k] for k in ref)
+
+
+def test_resnet_bn_folding_matches_batchnorm_eval():
+    """Host logic of the ResNet path: conv + eval BatchNorm == conv with folded weights + bias (packing is CPU-checkable)."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from medical_vision_langauge_transformer_b200.modules.visual_feature_extractor import _fold_bn
+    torch.manual_seed(0)
+    conv, bn = nn.Conv2d(8, 12, 3, stride=2, padding=1, bias=False), nn.BatchNorm2d(12).eval()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5), bn.bias.normal_(), bn.running_mean.normal_(), bn.running_var.uniform_(0.5, 2.0)
+        x = torch.randn(2, 8, 9, 9)
+        w, b = _fold_bn(conv, bn)
+        assert torch.allclose(F.conv2d(x, w, b, stride=2, padding=1), bn(conv(x)), atol=1e-5)
+
+
 def test_config_classes_mirror_reference_defaults():
     from medical_vision_langauge_transformer_b200.modules import config as C
     v, p, r = C.MVLBertConfigforVQA(), C.MVLBertPretrainConfig(), C.MVLBertRetrieval()

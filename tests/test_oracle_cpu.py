@@ -46,6 +46,21 @@ def test_oracle_retrieval_matches_reference_golden(case):
     _check_taps(taps, g["taps"])
 
 
+@pytest.mark.parametrize("conv", ["resnet101", "resnet50"])
+def test_oracle_resnet_retrieval_matches_reference_golden(conv):
+    """ResNet backbones (vfe.py:7-44 over torchvision's Bottleneck ResNet) + resnet_fc + the joint encoder."""
+    g = torch.load(os.path.join(GOLDEN, f"retrieval_{conv}.pt"))
+    sd = _sd(f"retrieval_{conv}", g["weight_seed"], g["flavour"])
+    x, ids = synth.synth_images(g["B"], g["data_seed"], g["img_scale"]), synth.synth_token_ids(g["B"], g["L"], g["data_seed"])
+    taps = {}
+    with torch.no_grad():
+        prob = O.retrieval_forward(sd, x, ids, taps=taps)
+        logits = O.retrieval_forward(sd, x, ids, return_logits=True)
+    assert torch.allclose(prob, g["prob"], atol=1e-6) and torch.allclose(logits, g["logits"], atol=1e-5)
+    assert {"stem", "layer1", "layer2", "layer3", "layer4"} <= set(taps)
+    _check_taps(taps, g["taps"])
+
+
 def test_oracle_vqa_matches_reference_golden():
     g = torch.load(os.path.join(GOLDEN, "vqa_stress.pt"))
     sd = _sd("vqa", g["weight_seed"], g["flavour"])
