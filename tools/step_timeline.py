@@ -9,10 +9,11 @@ from medical_vision_langauge_transformer_b200 import _lib, synth
 from medical_vision_langauge_transformer_b200.modules import config as C, model as M
 ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=64); ap.add_argument("--len", type=int, default=80)
 ap.add_argument("--reps", type=int, default=5); ap.add_argument("--detail", action="store_true")
+ap.add_argument("--conv", default="swintransformer")
 a = ap.parse_args()
 lib = _lib.ensure_init()
 torch.manual_seed(0)
-model = M.MVLBertForVQA(C.offline_config("vqa", max_length=a.len)).eval().to("cuda")
+model = M.MVLBertForVQA(C.offline_config("vqa", max_length=a.len, conv=a.conv)).eval().to("cuda")
 model.set_precision("bf16")
 x = synth.synth_images(a.batch, 1, 0.02).cuda(); ids = synth.synth_token_ids(a.batch, a.len, 1).cuda()
 names = [n for n in _lib.PROTOTYPES if n not in ("mvlt_init", "mvlt_abi_version")]
@@ -20,6 +21,8 @@ orig = {n: getattr(lib, n) for n in names}
 events, labels = [], []
 def label(n, args):
     if n == "mvlt_gemm_bf16_tc": return f"gemm {args[10]}x{args[11]}x{args[12]} act{args[13]} out{args[14]} res{int(args[7] is not None)}"
+    if n == "mvlt_conv2d_nhwc_bf16_tc":
+        return f"conv H{args[2]} C{args[4]} N{args[12]} k{args[13]} s{args[15]} act{args[17]} res{int(args[10] is not None)}"
     if n == "mvlt_layernorm_rows": return f"layernorm rows{args[8]} C{args[9]}"
     if n == "mvlt_window_attention": return f"window_attn H{args[5]} C{args[7]} shift{args[10]}"
     if n == "mvlt_swin_mlp_fused": return f"swin_mlp_fused M{args[9]} C{args[10]}"
