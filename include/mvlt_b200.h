@@ -62,10 +62,17 @@ int mvlt_conv2d_nhwc_bf16_tc(const void* x, int B, int H, int W, int C, const vo
 int mvlt_im2col_nhwc(const void* x, int dtype, void* out, long long ld_out, int B, int H, int W, int C, int R, int S,
                      int stride, int pad, mvlt_stream_t stream);
 
-/* Patch matrix of the ResNet stem (conv1 7x7/2 pad 3 on the 3-channel NCHW fp32 image, vfe.py:15 / resnet.py conv1):
+/* fp32 parity mode only: patch matrix of the ResNet stem (conv1 7x7/2 pad 3 on the 3-channel NCHW image, vfe.py:15):
  * out[B*Ho*Wo, kpad] (out_dtype), k = (c*R + ky)*S + kx = conv1.weight.view(64, -1) order, columns >= Cin*R*S zero. */
 int mvlt_stem_im2col_nchw(const float* img, void* out, int out_dtype, long long ld_out, int B, int Cin, int H, int W, int R,
                           int S, int stride, int pad, int kpad, mvlt_stream_t stream);
+
+/* The whole ResNet stem in one kernel (bf16 mode): conv1 7x7/2 pad 3 (3 -> 64 channels) + folded BatchNorm + ReLU +
+ * MaxPool2d(3, 2, 1); NCHW fp32 image [B,3,H,W] -> NHWC bf16 out [B, Hp, Wp, 64] (H = W = 224 -> 56 x 56).  w bf16 [64, 160]
+ * = conv1.weight.view(64, 147) * BatchNorm scale, zero padded; bias fp32 [64] = the folded shift.  mma.sync tiles over a
+ * shared-memory input patch; neither the patch matrix nor the 112 x 112 convolution output touches HBM.  vfe.py:15-18. */
+int mvlt_resnet_stem_tc(const float* img, const void* w, const float* bias, void* out, int B, int H, int W,
+                        mvlt_stream_t stream);
 
 /* nn.MaxPool2d(k, stride, pad) on NHWC (vfe.py:18: MaxPool2d(3, 2, 1) after the stem); dtype fp32|bf16. */
 int mvlt_maxpool_nhwc(const void* x, void* out, int dtype, int B, int H, int W, int C, int k, int stride, int pad,
@@ -149,6 +156,14 @@ int mvlt_softmax_rows(const float* in, float* out, long long rows, int N, mvlt_s
  * F.cross_entropy(..., ignore_index=-100) of model.py:410 and :418 (mean = [0]/[1]). */
 int mvlt_masked_ce_rows(const float* logits, long long ld, const long long* labels, float* loss_sum, long long rows,
                         int N, long long ignore_index, mvlt_stream_t stream);
+
+/* run_retrieval.py:220-249 `compute_ranks` on the device.  scores fp32 [R, C] (row stride lds) = the image x caption
+ * matching probabilities, labels uint8 [R, C] (1 = matching pair).  row_ranks int32 [R] (or NULL): position of the first
+ * matching caption of each image in descending-score order; col_ranks int32 [C] (or NULL): the same per caption over the
+ * images.  Equal scores are ordered by decreasing index (np.argsort(sim)[::-1] with a stable sort); a line without a
+ * positive ranks C (`num_captions_per_img`).  Two O(n) passes per line, no sort. */
+int mvlt_rank_first_positive(const float* scores, long long lds, const unsigned char* labels, long long ldl,
+                             int* row_ranks, int* col_ranks, int R, int C, mvlt_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,7 @@ PROTOTYPES = {
     "mvlt_conv2d_nhwc_bf16_tc": [_vp, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mvlt_im2col_nhwc": [_vp, _i, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mvlt_stem_im2col_nchw": [_vp, _vp, _i, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mvlt_resnet_stem_tc": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "mvlt_maxpool_nhwc": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mvlt_swin_mlp_fused": [_vp, _ll, _vp, _vp, _f, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp],
     "mvlt_gemm_f32_simt": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
@@ -33,6 +34,7 @@ PROTOTYPES = {
     "mvlt_joint_attention": [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _f, _vp],
     "mvlt_linear_small": [_vp, _i, _ll, _vp, _vp, _vp, _ll, _i, _i, _vp],
     "mvlt_softmax_rows": [_vp, _vp, _ll, _i, _vp],
+    "mvlt_rank_first_positive": [_vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _vp],
     "mvlt_masked_ce_rows": [_vp, _ll, _vp, _vp, _ll, _i, _ll, _vp],
 }
 

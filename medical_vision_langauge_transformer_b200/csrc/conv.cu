@@ -127,6 +127,170 @@ maxpool_nhwc_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// ResNet stem in one kernel (bf16 mode): conv1 7x7/2 pad 3 (3 -> 64) + folded BatchNorm + ReLU + MaxPool2d(3, 2, 1),
+// NCHW fp32 image -> NHWC bf16 [B, Hp, Wp, 64]  (vfe.py:15-18).  A CTA iteration owns a 4 x 7 tile of POOLED pixels:
+//   1. the 23 x 37 x 3 input patch behind it is staged in shared memory as bf16;
+//   2. nine warps each compute one row of 16 convolution outputs x 64 channels on mma.sync m16n8k16 (K = 147 padded to
+//      160): the A fragments are gathered from the patch through a per-thread table of (c, ky, kx) offsets held in
+//      registers, the packed weights [64, 160] stay in shared memory for the whole kernel (ldmatrix);
+//   3. bias + ReLU on the fragments, rows parked in shared memory (positions outside the image as 0 — equivalent to the
+//      -inf padding of the max-pool because every window holds at least one real, non-negative value);
+//   4. 3 x 3 / 2 max over the parked rows (bf16x2 max), 16-byte coalesced stores.
+// The 9 x 16 convolution tile recomputes one halo row / column per pooled tile (1.29x the MMAs, which are ~10 % of the
+// kernel's time); nothing but the image is read from and nothing but the pooled map is written to HBM.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int SP_ROWS = 4, SP_COLS = 7;                         // pooled tile
+constexpr int SC_ROWS = 2 * SP_ROWS + 1, SC_COLS = 16;          // convolution tile (15 columns used)
+constexpr int SI_ROWS = 2 * (SC_ROWS - 1) + 7, SI_COLS = 2 * (SC_COLS - 1) + 7, SI_LD = 40;   // 23 x 37 input patch
+constexpr int SK = 3 * 7 * 7, SKP = 160, SW_LD = 168, SO_LD = 72, STEM_N = 64;
+constexpr int STEM_THREADS = SC_ROWS * 32;
+constexpr int STEM_SMEM = (STEM_N * SW_LD + 3 * SI_ROWS * SI_LD + SC_ROWS * SC_COLS * SO_LD) * 2 + STEM_N * 4;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t stem_koff(int k) {   // patch offset of filter element k = (c*7 + ky)*7 + kx
+  if (k >= SK) return 0;                                  // zero-weight padding columns: any finite value will do
+  const int c = k / 49, r = k - c * 49, ky = r / 7, kx = r - ky * 7;
+  return (uint32_t)((c * SI_ROWS + ky) * SI_LD + kx);
+}
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+constexpr int STEM_PATCH_ELEMS = 3 * SI_ROWS * SI_COLS, STEM_PF = (STEM_PATCH_ELEMS + STEM_THREADS - 1) / STEM_THREADS;
+__device__ __forceinline__ void stem_prefetch(float (&pf)[STEM_PF], const float* __restrict__ img, int tile, int tiles_x,
+                                              int tiles_y, int H, int W, int tid) {
+  const int b = tile / (tiles_y * tiles_x), tr = tile - b * tiles_y * tiles_x;
+  const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
+  const int iy0 = 2 * (2 * ty * SP_ROWS - 1) - 3, ix0 = 2 * (2 * tx * SP_COLS - 1) - 3;
+#pragma unroll
+  for (int j = 0; j < STEM_PF; ++j) {
+    const int i = tid + j * STEM_THREADS;
+    const int c = i / (SI_ROWS * SI_COLS), r2 = i - c * (SI_ROWS * SI_COLS);
+    const int r = r2 / SI_COLS, col = r2 - r * SI_COLS;
+    const int iy = iy0 + r, ix = ix0 + col;
+    pf[j] = (i < STEM_PATCH_ELEMS && iy >= 0 && iy < H && ix >= 0 && ix < W)
+                ? __ldg(img + (((long long)b * 3 + c) * H + iy) * W + ix) : 0.f;
+  }
+}
+
+__global__ void __maxnreg__(112)
+resnet_stem_tc_kernel(const float* __restrict__ img, const bf16* __restrict__ w, const float* __restrict__ bias,
+                      bf16* __restrict__ out, int B, int H, int W, int Ho, int Wo, int Hp, int Wp) {
+  extern __shared__ __align__(16) uint8_t smem_stem[];
+  bf16* wsm = reinterpret_cast<bf16*>(smem_stem);                 // [64][SW_LD]
+  bf16* patch = wsm + STEM_N * SW_LD;                             // [3][SI_ROWS][SI_LD]
+  bf16* stage = patch + 3 * SI_ROWS * SI_LD;                      // [SC_ROWS][SC_COLS][SO_LD]
+  float* sbias = reinterpret_cast<float*>(stage + SC_ROWS * SC_COLS * SO_LD);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  // filter-element offsets of this thread's A-fragment columns: k = 16*ks + 2t + {0, 1, 8, 9}
+  uint32_t kp[SKP / 16][2];
+#pragma unroll
+  for (int ks = 0; ks < SKP / 16; ++ks) {
+    const int k0 = ks * 16 + 2 * t;
+    kp[ks][0] = stem_koff(k0) | (stem_koff(k0 + 1) << 16);
+    kp[ks][1] = stem_koff(k0 + 8) | (stem_koff(k0 + 9) << 16);
+  }
+  pdl_grid_sync();
+  for (int i = tid; i < STEM_N * (SKP / 8); i += STEM_THREADS) {
+    const int n = i / (SKP / 8), c8 = i - n * (SKP / 8);
+    *reinterpret_cast<uint4*>(wsm + n * SW_LD + c8 * 8) = *reinterpret_cast<const uint4*>(w + n * SKP + c8 * 8);
+  }
+  if (tid < STEM_N) sbias[tid] = bias[tid];
+
+  const int tiles_x = (Wp + SP_COLS - 1) / SP_COLS, tiles_y = (Hp + SP_ROWS - 1) / SP_ROWS;
+  const int tiles = B * tiles_y * tiles_x;
+  const unsigned short* patch16 = reinterpret_cast<const unsigned short*>(patch);
+  // The input patch of the NEXT tile is fetched into registers while the current tile computes (all loads of a thread in
+  // flight together), and written to shared memory at the top of the next iteration.
+  float pf[STEM_PF];
+  auto prefetch = [&](int tile) { stem_prefetch(pf, img, tile, tiles_x, tiles_y, H, W, tid); };
+  if (blockIdx.x < tiles) prefetch(blockIdx.x);
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int b = tile / (tiles_y * tiles_x), tr = tile - b * tiles_y * tiles_x;
+    const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
+    const int py0 = ty * SP_ROWS, px0 = tx * SP_COLS;            // first pooled pixel
+    const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;              // first convolution pixel (halo row / column)
+    __syncthreads();                                              // previous iteration's pooling has read `stage`; weights landed
+#pragma unroll
+    for (int j = 0; j < STEM_PF; ++j) {
+      const int i = tid + j * STEM_THREADS;
+      if (i < STEM_PATCH_ELEMS) {
+        const int c = i / (SI_ROWS * SI_COLS), r2 = i - c * (SI_ROWS * SI_COLS);
+        const int r = r2 / SI_COLS, col = r2 - r * SI_COLS;
+        patch[(c * SI_ROWS + r) * SI_LD + col] = __float2bfloat16_rn(pf[j]);
+      }
+    }
+    __syncthreads();
+    if (tile + (int)gridDim.x < tiles) prefetch(tile + gridDim.x);
+
+    // ---- convolution row `warp` of the tile: 16 pixels x 64 channels
+    float acc[STEM_N / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < STEM_N / 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    const uint32_t base0 = (uint32_t)(2 * warp * SI_LD + 2 * g), base1 = base0 + 16;   // pixels g and g + 8 of the row
+    const uint32_t wbase = smem_u32(wsm + ((lane >> 4) * 8 + (lane & 7)) * SW_LD + ((lane >> 3) & 1) * 8);
+#pragma unroll
+    for (int ks = 0; ks < SKP / 16; ++ks) {
+      const uint32_t o0 = kp[ks][0] & 0xffffu, o1 = kp[ks][0] >> 16, o2 = kp[ks][1] & 0xffffu, o3 = kp[ks][1] >> 16;
+      const uint32_t a0 = patch16[base0 + o0] | ((uint32_t)patch16[base0 + o1] << 16);
+      const uint32_t a1 = patch16[base1 + o0] | ((uint32_t)patch16[base1 + o1] << 16);
+      const uint32_t a2 = patch16[base0 + o2] | ((uint32_t)patch16[base0 + o3] << 16);
+      const uint32_t a3 = patch16[base1 + o2] | ((uint32_t)patch16[base1 + o3] << 16);
+#pragma unroll
+      for (int np = 0; np < STEM_N / 16; ++np) {
+        uint32_t b0, b1, b2, b3;   // (n-tile 2np: k lo, k hi), (n-tile 2np+1: k lo, k hi)
+        ldsm_x4(wbase + (uint32_t)((np * 16 * SW_LD + ks * 16) * 2), b0, b1, b2, b3);
+        mma_bf16_16816(acc[2 * np], a0, a1, a2, a3, b0, b1);
+        mma_bf16_16816(acc[2 * np + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+    // ---- bias + ReLU, park the row (0 outside the image)
+    const int cy = cy0 + warp;
+    const bool row_ok = cy >= 0 && cy < Ho;
+    const bool ok0 = row_ok && cx0 + g >= 0 && cx0 + g < Wo, ok1 = row_ok && cx0 + g + 8 >= 0 && cx0 + g + 8 < Wo;
+    bf16* srow = stage + warp * SC_COLS * SO_LD;
+#pragma unroll
+    for (int nt = 0; nt < STEM_N / 8; ++nt) {
+      const float2 bb = *reinterpret_cast<const float2*>(sbias + nt * 8 + 2 * t);
+      const uint32_t v0 = ok0 ? pack_bf16x2(fmaxf(acc[nt][0] + bb.x, 0.f), fmaxf(acc[nt][1] + bb.y, 0.f)) : 0u;
+      const uint32_t v1 = ok1 ? pack_bf16x2(fmaxf(acc[nt][2] + bb.x, 0.f), fmaxf(acc[nt][3] + bb.y, 0.f)) : 0u;
+      *reinterpret_cast<uint32_t*>(srow + g * SO_LD + nt * 8 + 2 * t) = v0;
+      *reinterpret_cast<uint32_t*>(srow + (g + 8) * SO_LD + nt * 8 + 2 * t) = v1;
+    }
+    __syncthreads();
+    // ---- 3x3/2 max-pool over the parked rows: one (pooled pixel, 8-channel chunk) per thread
+    if (tid < SP_ROWS * SP_COLS * 8) {
+      const int pp = tid >> 3, c8 = tid & 7;
+      const int pr = pp / SP_COLS, pc = pp - pr * SP_COLS;
+      const int py = py0 + pr, px = px0 + pc;
+      if (py < Hp && px < Wp) {
+        uint4 m = make_uint4(0, 0, 0, 0);   // values are >= 0
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const uint4 v = *reinterpret_cast<const uint4*>(stage + ((2 * pr + dy) * SC_COLS + 2 * pc + dx) * SO_LD + c8 * 8);
+            m.x = bf16x2_max(m.x, v.x); m.y = bf16x2_max(m.y, v.y); m.z = bf16x2_max(m.z, v.z); m.w = bf16x2_max(m.w, v.w);
+          }
+        *reinterpret_cast<uint4*>(out + (((long long)b * Hp + py) * Wp + px) * STEM_N + c8 * 8) = m;
+      }
+    }
+  }
+}
+
 static inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 32;   // grid-stride: 32 CTAs of 256 threads per SM is already more than resident
@@ -184,6 +348,30 @@ extern "C" int mvlt_stem_im2col_nchw(const float* img, void* out, int out_dtype,
   } else {
     return MVLT_ERR_INVALID;
   }
+  MVLT_LAUNCH_CHECK();
+  return MVLT_OK;
+}
+
+extern "C" int mvlt_resnet_stem_tc(const float* img, const void* w, const float* bias, void* out, int B, int H, int W,
+                                   cudaStream_t stream) {
+  if (!img || !w || !bias || !out || B <= 0 || H < 7 || W < 7) return MVLT_ERR_INVALID;
+  if (((uintptr_t)w & 15) || ((uintptr_t)out & 15) || ((uintptr_t)bias & 7)) return MVLT_ERR_INVALID;
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;        // conv1: k 7, stride 2, pad 3
+  const int Hp = (Ho + 2 - 3) / 2 + 1, Wp = (Wo + 2 - 3) / 2 + 1;      // maxpool: k 3, stride 2, pad 1
+  const long long tiles = (long long)B * ((Hp + SP_ROWS - 1) / SP_ROWS) * ((Wp + SP_COLS - 1) / SP_COLS);
+  if (tiles > 0x7fffffffLL) return MVLT_ERR_UNSUPPORTED;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(resnet_stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(tiles < 2LL * sms ? tiles : 2LL * sms);        // persistent: 2 CTAs per SM, weights staged once
+  launch_k(resnet_stem_tc_kernel, dim3(grid), dim3(STEM_THREADS), STEM_SMEM, stream, img, (const bf16*)w, bias, (bf16*)out, B,
+           H, W, Ho, Wo, Hp, Wp);
   MVLT_LAUNCH_CHECK();
   return MVLT_OK;
 }

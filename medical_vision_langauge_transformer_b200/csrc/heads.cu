@@ -3,6 +3,8 @@
 //                       ITM Linear(768,2) model.py:363 (and any N <= 16 head)
 //   mvlt_softmax_rows   model.py:348 (VQA softmax over result_num), model.py:468 (retrieval softmax over 2)
 //   mvlt_masked_ce_rows F.cross_entropy(ignore_index=-100) over fp32 logits rows, model.py:410,:418
+//   mvlt_rank_first_positive  run_retrieval.py:220-249 `compute_ranks` on the device: per image row (and per caption
+//                       column) the position of the best-placed positive in descending-score order
 #include "common.cuh"
 
 namespace mvlt {
@@ -69,6 +71,56 @@ masked_ce_rows_kernel(const float* __restrict__ logits, long long ld, const long
   }
 }
 
+// Position of the first positive of one line of the score matrix in descending order.  np.argsort(sim)[::-1] lists equal
+// scores by DEcreasing index (stable ascending sort, reversed), so the order is the lexicographic key (score, index)
+// descending: the first positive is the positive with the largest key and its rank is the number of elements with a
+// larger key — two O(n) passes, no sort.  LINE_IS_ROW: one warp per row (coalesced along the row); otherwise one thread
+// per column (adjacent threads read adjacent columns).
+__device__ __forceinline__ bool key_gt(float s, int j, float s0, int j0) { return s > s0 || (s == s0 && j > j0); }
+
+__global__ void __launch_bounds__(256)
+rank_rows_kernel(const float* __restrict__ scores, long long lds, const unsigned char* __restrict__ labels, long long ldl,
+                 int* __restrict__ out, int R, int C, int none) {
+  pdl_grid_sync();
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* s = scores + (long long)row * lds;
+  const unsigned char* l = labels + (long long)row * ldl;
+  float bs = -INFINITY;
+  int bj = -1;
+  for (int j = lane; j < C; j += 32)
+    if (l[j] == 1 && (bj < 0 || key_gt(s[j], j, bs, bj))) { bs = s[j]; bj = j; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+    if (oj >= 0 && (bj < 0 || key_gt(os, oj, bs, bj))) { bs = os; bj = oj; }
+  }
+  int cnt = 0;
+  if (bj >= 0)
+    for (int j = lane; j < C; j += 32) cnt += key_gt(s[j], j, bs, bj) ? 1 : 0;
+  cnt = (int)warp_sum((float)cnt);   // exact for counts < 2^24
+  if (lane == 0) out[row] = bj >= 0 ? cnt : none;
+}
+
+__global__ void __launch_bounds__(128)
+rank_cols_kernel(const float* __restrict__ scores, long long lds, const unsigned char* __restrict__ labels, long long ldl,
+                 int* __restrict__ out, int R, int C, int none) {
+  pdl_grid_sync();
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= C) return;
+  float bs = -INFINITY;
+  int bi = -1;
+  for (int i = 0; i < R; ++i) {
+    const float v = scores[(long long)i * lds + col];
+    if (labels[(long long)i * ldl + col] == 1 && (bi < 0 || key_gt(v, i, bs, bi))) { bs = v; bi = i; }
+  }
+  int cnt = 0;
+  if (bi >= 0)
+    for (int i = 0; i < R; ++i) cnt += key_gt(scores[(long long)i * lds + col], i, bs, bi) ? 1 : 0;
+  out[col] = bi >= 0 ? cnt : none;
+}
+
 }  // namespace mvlt
 
 using namespace mvlt;
@@ -98,5 +150,20 @@ extern "C" int mvlt_masked_ce_rows(const float* logits, long long ld, const long
   if (e != cudaSuccess) return (int)e;
   launch_k(masked_ce_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, stream, logits, ld, labels, loss_sum, rows, N, ignore_index);
   MVLT_LAUNCH_CHECK();
+  return MVLT_OK;
+}
+
+extern "C" int mvlt_rank_first_positive(const float* scores, long long lds, const unsigned char* labels, long long ldl,
+                                        int* row_ranks, int* col_ranks, int R, int C, cudaStream_t stream) {
+  if (!scores || !labels || R <= 0 || C <= 0 || lds < C || ldl < C || (!row_ranks && !col_ranks)) return MVLT_ERR_INVALID;
+  if (R >= (1 << 24) || C >= (1 << 24)) return MVLT_ERR_UNSUPPORTED;
+  if (row_ranks) {   // a row without a positive ranks `C`, a column without one `C` as well (run_retrieval.py:230,:242)
+    mvlt::launch_k(mvlt::rank_rows_kernel, dim3((R + 7) / 8), dim3(256), 0, stream, scores, lds, labels, ldl, row_ranks, R, C, C);
+    MVLT_LAUNCH_CHECK();
+  }
+  if (col_ranks) {
+    mvlt::launch_k(mvlt::rank_cols_kernel, dim3((C + 127) / 128), dim3(128), 0, stream, scores, lds, labels, ldl, col_ranks, R, C, C);
+    MVLT_LAUNCH_CHECK();
+  }
   return MVLT_OK;
 }

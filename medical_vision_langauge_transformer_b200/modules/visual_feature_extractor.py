@@ -329,8 +329,8 @@ class ResNetWithoutFC(nn.Module):
     Initialisation as torchvision: kaiming-normal (fan_out, relu) convolutions, unit BatchNorm.  Eval-mode BatchNorm only
     (running statistics folded into the GEMM weights): this is the forward path; `train()` statistics are out of scope.
 
-    Arithmetic: activations are NHWC matrices [B*H*W, C] (bf16 in bf16 mode); the stem is a patch-matrix kernel + GEMM,
-    1x1 convolutions are tcgen05 GEMMs on the matrix as is, 3x3 and strided convolutions are the same GEMM kernel with its
+    Arithmetic: activations are NHWC matrices [B*H*W, C] (bf16 in bf16 mode); the stem (conv1 + bn1 + relu + maxpool) is
+    one mma.sync kernel, 1x1 convolutions are tcgen05 GEMMs on the matrix as is, 3x3 and strided convolutions are the same GEMM kernel with its
     A operand fetched by im2col-mode TMA, BatchNorm + ReLU + the identity add live in the GEMM epilogue."""
 
     def __init__(self, layers, pretrained=False, progress=False, precision=None, num_classes=1000):
@@ -417,11 +417,14 @@ class ResNetWithoutFC(nn.Module):
         pk = self.packed()
         adt = act_dtype(self.precision)
         x = x.contiguous().float()
-        a = ops.stem_im2col(x, 7, 7, 2, 3, self.STEM_KPAD, adt)
-        a = ops.linear(a, pk["stem_w"], pk["stem_b"], act=ops.ACT_RELU)
-        H, W = ops.conv_out_hw(H, W, 7, 7, 2, 3)
-        a = ops.maxpool_nhwc(a, B, H, W, 3, 2, 1)
-        H, W = ops.conv_out_hw(H, W, 3, 3, 2, 1)
+        if self.precision == "bf16":     # conv1 + bn1 + relu + maxpool as one tensor-core kernel
+            a, H, W = ops.resnet_stem(x, pk["stem_w"], pk["stem_b"])
+        else:                            # parity mode: patch matrix + CUDA-core GEMM + max-pool kernel
+            a = ops.stem_im2col(x, 7, 7, 2, 3, self.STEM_KPAD, adt)
+            a = ops.linear(a, pk["stem_w"], pk["stem_b"], act=ops.ACT_RELU)
+            H, W = ops.conv_out_hw(H, W, 7, 7, 2, 3)
+            a = ops.maxpool_nhwc(a, B, H, W, 3, 2, 1)
+            H, W = ops.conv_out_hw(H, W, 3, 3, 2, 1)
         taps = self.taps
         if taps is not None:
             taps["stem"] = a.float().view(B, H, W, -1).permute(0, 3, 1, 2).clone()

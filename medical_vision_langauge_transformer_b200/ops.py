@@ -124,6 +124,22 @@ def stem_im2col(img: torch.Tensor, R: int, S: int, stride: int, pad: int, kpad: 
     return out
 
 
+def resnet_stem(img: torch.Tensor, w: torch.Tensor, bias: torch.Tensor):
+    """conv1 7x7/2 + folded BatchNorm + ReLU + MaxPool2d(3,2,1) in one kernel (bf16 mode).
+    img fp32 NCHW [B,3,H,W]; w bf16 [64,160]; bias fp32 [64] -> (NHWC bf16 [B*Hp*Wp, 64], Hp, Wp)."""
+    lib = _lib.ensure_init()
+    assert img.dtype == torch.float32 and img.is_contiguous() and img.dim() == 4 and img.shape[1] == 3
+    assert w.dtype == torch.bfloat16 and w.shape == (64, 160) and w.is_contiguous()
+    assert bias.dtype == torch.float32 and bias.numel() == 64 and bias.is_contiguous()
+    B, _, H, W = img.shape
+    Ho, Wo = conv_out_hw(H, W, 7, 7, 2, 3)
+    Hp, Wp = conv_out_hw(Ho, Wo, 3, 3, 2, 1)
+    out = torch.empty((B * Hp * Wp, 64), device=img.device, dtype=torch.bfloat16)
+    rc = lib.mvlt_resnet_stem_tc(img.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), B, H, W, _stream())
+    _lib.check(rc, "mvlt_resnet_stem_tc")
+    return out, Hp, Wp
+
+
 def maxpool_nhwc(x: torch.Tensor, B: int, H: int, W: int, k: int, stride: int, pad: int) -> torch.Tensor:
     lib = _lib.ensure_init()
     rows, C, ld = _rows2d(x)
@@ -330,3 +346,18 @@ def masked_ce(logits: torch.Tensor, labels: torch.Tensor, n_classes: int, ignore
                                  ignore_index, _stream())
     _lib.check(rc, "mvlt_masked_ce_rows")
     return acc
+
+
+def rank_first_positive(scores: torch.Tensor, labels: torch.Tensor):
+    """compute_ranks of run_retrieval.py:220-249 on the device -> (row ranks int32 [R], column ranks int32 [C])."""
+    lib = _lib.ensure_init()
+    assert scores.is_cuda and scores.dtype == torch.float32 and scores.dim() == 2 and scores.stride(1) == 1
+    lab = labels.to(device=scores.device).eq(1).to(torch.uint8).contiguous()
+    R, C = scores.shape
+    assert lab.shape == (R, C)
+    rows = torch.empty(R, device=scores.device, dtype=torch.int32)
+    cols = torch.empty(C, device=scores.device, dtype=torch.int32)
+    rc = lib.mvlt_rank_first_positive(scores.data_ptr(), scores.stride(0), lab.data_ptr(), C, rows.data_ptr(), cols.data_ptr(),
+                                      R, C, _stream())
+    _lib.check(rc, "mvlt_rank_first_positive")
+    return rows, cols

@@ -80,8 +80,19 @@ def all_gather_scores(local: torch.Tensor, n_rows: int, world: int, group=None) 
 
 
 def compute_ranks(scores, labels):
-    """run_retrieval.py:220-249: per image row the position of the first matching caption in descending-score order
-    (numpy argsort reversed, so ties break exactly as in the reference); then per caption column. -> (i2t, t2i)."""
+    """run_retrieval.py:220-249: per image row the position of the first matching caption in descending-score order, then
+    per caption column. -> (i2t, t2i) as Python lists.  A CUDA score matrix (what `score_matrix` / `all_gather_scores`
+    return) is ranked on the device (`mvlt_rank_first_positive`: two passes per line, no sort, no [N,N] D2H copy); host
+    arrays take the reference's own numpy route."""
+    if torch.is_tensor(scores) and scores.is_cuda:
+        lab = labels if torch.is_tensor(labels) else torch.as_tensor(np.asarray(labels))
+        rows, cols = ops.rank_first_positive(scores.float().contiguous(), lab)
+        return rows.tolist(), cols.tolist()
+    return compute_ranks_host(scores, labels)
+
+
+def compute_ranks_host(scores, labels):
+    """The reference's numpy algorithm for host arrays (np.argsort reversed; ties as numpy breaks them)."""
     scores = np.asarray(scores.detach().cpu() if torch.is_tensor(scores) else scores)
     labels = np.asarray(labels.detach().cpu() if torch.is_tensor(labels) else labels)
     n = scores.shape[1]

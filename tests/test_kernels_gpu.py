@@ -299,3 +299,41 @@ def test_heads(cuda):
     ref = F.cross_entropy(lg, labels, ignore_index=-100, reduction="sum")
     assert abs(acc[0].item() - ref.item()) < 1e-3 * abs(ref.item())
     assert acc[1].item() == (labels != -100).sum().item()
+
+
+@pytest.mark.parametrize("R,C", [(6, 6), (257, 300), (2000, 2000)])
+def test_rank_first_positive_device(cuda, R, C):
+    """Device-side compute_ranks (run_retrieval.py:220-249) vs the reference's numpy loop: planted diagonal positives plus
+    duplicates, lines without any positive, and exact score ties (np.argsort(kind='stable')[::-1] order)."""
+    import numpy as np
+    from medical_vision_langauge_transformer_b200 import ops
+    g = torch.Generator().manual_seed(R * 31 + C)
+    scores = torch.rand(R, C, generator=g)
+    scores[torch.rand(R, C, generator=g) < 0.2] = 0.5            # ties, also between positives and negatives
+    labels = torch.zeros(R, C, dtype=torch.long)
+    d = min(R, C)
+    labels[torch.arange(d), torch.arange(d)] = 1
+    labels[1, min(4, C - 1)] = labels[min(4, R - 1), 1] = 1      # duplicate caption ids (run_retrieval.py:139)
+    labels[2, :] = 0                                             # an image without a matching caption
+    labels[:, 3] = 0
+
+    def ref(sim, lab):
+        out = []
+        for s, l in zip(sim, lab):
+            hit = np.nonzero(l[np.argsort(s, kind="stable")[::-1]] == 1)[0]
+            out.append(int(hit[0]) if hit.size else sim.shape[1])
+        return out
+
+    rows, cols = ops.rank_first_positive(scores.cuda(), labels.cuda())
+    s, l = scores.numpy(), labels.numpy()
+    assert rows.tolist() == ref(s, l)
+    assert cols.tolist() == _col_ref(s, l, C)
+
+
+def _col_ref(s, l, none):
+    import numpy as np
+    out = []
+    for sc, lc in zip(s.T, l.T):
+        hit = np.nonzero(lc[np.argsort(sc, kind="stable")[::-1]] == 1)[0]
+        out.append(int(hit[0]) if hit.size else none)
+    return out

@@ -111,6 +111,23 @@ def test_stem_im2col_and_maxpool(cuda, dtype):
     assert torch.equal(out.float(), nhwc(F.max_pool2d(x.float(), 3, 2, 1)))
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 224, 224), (1, 64, 96), (3, 46, 30)])
+def test_resnet_stem_fused(cuda, B, H, W):
+    """conv1 7x7/2 + folded bn1 + relu + maxpool 3x3/2 in one kernel vs torch on the same bf16-rounded operands; ragged
+    sizes exercise partial pooled tiles and the halo rows / columns outside the image."""
+    from medical_vision_langauge_transformer_b200 import ops
+    img = rnd(B, 3, H, W, seed=12)
+    w = rnd(64, 3, 7, 7, seed=13, scale=1 / math.sqrt(147))
+    bias = rnd(64, seed=14, scale=0.2)
+    wp = torch.zeros(64, 160, device="cuda")
+    wp[:, :147] = w.reshape(64, 147)
+    out, Hp, Wp = ops.resnet_stem(img, wp.bfloat16().contiguous(), bias)
+    conv = F.conv2d(img.bfloat16().float(), w.bfloat16().float(), bias, stride=2, padding=3)
+    ref = F.max_pool2d(F.relu(conv).bfloat16().float(), 3, 2, 1)
+    assert (Hp, Wp) == tuple(ref.shape[2:]) and out.shape == (B * Hp * Wp, 64)
+    assert relerr(out, nhwc(ref)) < 1e-2
+
+
 def test_im2col_explicit(cuda):
     """The parity-mode patch matrix is tap-major: k = (ky*S + kx)*C + c."""
     from medical_vision_langauge_transformer_b200 import _lib, ops
