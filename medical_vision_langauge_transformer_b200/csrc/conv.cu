@@ -129,22 +129,25 @@ maxpool_nhwc_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, 
 
 // ---------------------------------------------------------------------------------------------------------------------
 // ResNet stem in one kernel (bf16 mode): conv1 7x7/2 pad 3 (3 -> 64) + folded BatchNorm + ReLU + MaxPool2d(3, 2, 1),
-// NCHW fp32 image -> NHWC bf16 [B, Hp, Wp, 64]  (vfe.py:15-18).  A CTA iteration owns a 4 x 7 tile of POOLED pixels:
-//   1. the 23 x 37 x 3 input patch behind it is staged in shared memory as bf16;
-//   2. nine warps each compute one row of 16 convolution outputs x 64 channels on mma.sync m16n8k16 (K = 147 padded to
-//      160): the A fragments are gathered from the patch through a per-thread table of (c, ky, kx) offsets held in
-//      registers, the packed weights [64, 160] stay in shared memory for the whole kernel (ldmatrix);
+// NCHW fp32 image -> NHWC bf16 [B, Hp, Wp, 64]  (vfe.py:15-18).  A CTA iteration owns a 3 x 7 tile of POOLED pixels:
+//   1. the 19 x 37 x 3 input patch behind it is staged in shared memory as bf16 (fetched into registers one tile ahead);
+//   2. seven warps each compute one row of 16 convolution outputs x 64 channels on mma.sync m16n8k16.  K is laid out as
+//      (c, ky, kx padded 7 -> 8) = 168, rounded up to 176: a k-pair (kx, kx+1) with kx even is ONE aligned 32-bit word of
+//      the patch (input column 2*x + kx is even), so an A fragment register is a single LDS.32 through a per-thread table
+//      of patch offsets held in registers; the weights are re-laid out to [64, 176] (zeros in the padding) while they are
+//      staged in shared memory, where they stay for the whole kernel (ldmatrix);
 //   3. bias + ReLU on the fragments, rows parked in shared memory (positions outside the image as 0 — equivalent to the
 //      -inf padding of the max-pool because every window holds at least one real, non-negative value);
 //   4. 3 x 3 / 2 max over the parked rows (bf16x2 max), 16-byte coalesced stores.
-// The 9 x 16 convolution tile recomputes one halo row / column per pooled tile (1.29x the MMAs, which are ~10 % of the
-// kernel's time); nothing but the image is read from and nothing but the pooled map is written to HBM.
+// The 7 x 16 convolution tile recomputes one halo row / column per pooled tile (1.33x the MMAs); nothing but the image is
+// read from and nothing but the pooled map is written to HBM.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int SP_ROWS = 4, SP_COLS = 7;                         // pooled tile
+constexpr int SP_ROWS = 3, SP_COLS = 7;                         // pooled tile
 constexpr int SC_ROWS = 2 * SP_ROWS + 1, SC_COLS = 16;          // convolution tile (15 columns used)
-constexpr int SI_ROWS = 2 * (SC_ROWS - 1) + 7, SI_COLS = 2 * (SC_COLS - 1) + 7, SI_LD = 40;   // 23 x 37 input patch
-constexpr int SK = 3 * 7 * 7, SKP = 160, SW_LD = 168, SO_LD = 72, STEM_N = 64;
-constexpr int STEM_THREADS = SC_ROWS * 32;
+constexpr int SI_ROWS = 2 * (SC_ROWS - 1) + 7, SI_COLS = 2 * (SC_COLS - 1) + 7, SI_LD = 40;   // 19 x 37 input patch
+constexpr int SK = 3 * 7 * 7, SK_IN = 160;                      // filter elements; row length of the packed weights in HBM
+constexpr int SK8 = 3 * 7 * 8, SKP = 176, SW_LD = 184, SO_LD = 72, STEM_N = 64;   // kx-padded K, smem row strides
+constexpr int STEM_THREADS = 256;   // 8 warps (warps are allocated in fours: 9 would cost the registers of 12); 7 of them run MMAs
 constexpr int STEM_SMEM = (STEM_N * SW_LD + 3 * SI_ROWS * SI_LD + SC_ROWS * SC_COLS * SO_LD) * 2 + STEM_N * 4;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -157,10 +160,11 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint3
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t stem_koff(int k) {   // patch offset of filter element k = (c*7 + ky)*7 + kx
-  if (k >= SK) return 0;                                  // zero-weight padding columns: any finite value will do
-  const int c = k / 49, r = k - c * 49, ky = r / 7, kx = r - ky * 7;
-  return (uint32_t)((c * SI_ROWS + ky) * SI_LD + kx);
+// patch offset, in 32-bit words, of the k-pair starting at the (even) padded filter index k = (c*7 + ky)*8 + kx
+__device__ __forceinline__ uint32_t stem_koff(int k) {
+  if (k >= SK8) return 0;                                 // zero-weight padding: any finite value will do
+  const int c = k / 56, r = k - c * 56, ky = r >> 3, kx = r & 7;
+  return (uint32_t)(((c * SI_ROWS + ky) * SI_LD + kx) >> 1);
 }
 __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
   __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
@@ -168,56 +172,63 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 }
 
 constexpr int STEM_PATCH_ELEMS = 3 * SI_ROWS * SI_COLS, STEM_PF = (STEM_PATCH_ELEMS + STEM_THREADS - 1) / STEM_THREADS;
-__device__ __forceinline__ void stem_prefetch(float (&pf)[STEM_PF], const float* __restrict__ img, int tile, int tiles_x,
-                                              int tiles_y, int H, int W, int tid) {
+// pe[j] packs (patch index << 16 | c << 12 | r << 6 | col) of the j-th patch element this thread fetches; 0xffffffff = none
+__device__ __forceinline__ void stem_prefetch(float (&pf)[STEM_PF], const uint32_t (&pe)[STEM_PF], const float* __restrict__ img,
+                                              int tile, int tiles_x, int tiles_y, int H, int W) {
   const int b = tile / (tiles_y * tiles_x), tr = tile - b * tiles_y * tiles_x;
   const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
   const int iy0 = 2 * (2 * ty * SP_ROWS - 1) - 3, ix0 = 2 * (2 * tx * SP_COLS - 1) - 3;
+  const float* base = img + (long long)b * 3 * H * W;
 #pragma unroll
   for (int j = 0; j < STEM_PF; ++j) {
-    const int i = tid + j * STEM_THREADS;
-    const int c = i / (SI_ROWS * SI_COLS), r2 = i - c * (SI_ROWS * SI_COLS);
-    const int r = r2 / SI_COLS, col = r2 - r * SI_COLS;
-    const int iy = iy0 + r, ix = ix0 + col;
-    pf[j] = (i < STEM_PATCH_ELEMS && iy >= 0 && iy < H && ix >= 0 && ix < W)
-                ? __ldg(img + (((long long)b * 3 + c) * H + iy) * W + ix) : 0.f;
+    const int c = (pe[j] >> 12) & 3, iy = iy0 + (int)((pe[j] >> 6) & 63), ix = ix0 + (int)(pe[j] & 63);
+    pf[j] = (pe[j] != 0xffffffffu && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(base + ((long long)c * H + iy) * W + ix) : 0.f;
   }
 }
 
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(STEM_THREADS, 2)
 resnet_stem_tc_kernel(const float* __restrict__ img, const bf16* __restrict__ w, const float* __restrict__ bias,
                       bf16* __restrict__ out, int B, int H, int W, int Ho, int Wo, int Hp, int Wp) {
   extern __shared__ __align__(16) uint8_t smem_stem[];
-  bf16* wsm = reinterpret_cast<bf16*>(smem_stem);                 // [64][SW_LD]
+  bf16* wsm = reinterpret_cast<bf16*>(smem_stem);                 // [64][SW_LD], k = (c*7 + ky)*8 + kx
   bf16* patch = wsm + STEM_N * SW_LD;                             // [3][SI_ROWS][SI_LD]
   bf16* stage = patch + 3 * SI_ROWS * SI_LD;                      // [SC_ROWS][SC_COLS][SO_LD]
   float* sbias = reinterpret_cast<float*>(stage + SC_ROWS * SC_COLS * SO_LD);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
 
-  // filter-element offsets of this thread's A-fragment columns: k = 16*ks + 2t + {0, 1, 8, 9}
-  uint32_t kp[SKP / 16][2];
+  // word offsets of this thread's A-fragment k-pairs: k = 16*ks + 2t (+1) and 16*ks + 2t + 8 (+1)
+  uint32_t kp[SKP / 16];
 #pragma unroll
-  for (int ks = 0; ks < SKP / 16; ++ks) {
-    const int k0 = ks * 16 + 2 * t;
-    kp[ks][0] = stem_koff(k0) | (stem_koff(k0 + 1) << 16);
-    kp[ks][1] = stem_koff(k0 + 8) | (stem_koff(k0 + 9) << 16);
+  for (int ks = 0; ks < SKP / 16; ++ks) kp[ks] = stem_koff(ks * 16 + 2 * t) | (stem_koff(ks * 16 + 2 * t + 8) << 16);
+  uint32_t pe[STEM_PF];
+#pragma unroll
+  for (int j = 0; j < STEM_PF; ++j) {
+    const int i = tid + j * STEM_THREADS;
+    const int c = i / (SI_ROWS * SI_COLS), r2 = i - c * (SI_ROWS * SI_COLS);
+    const int r = r2 / SI_COLS, col = r2 - r * SI_COLS;
+    pe[j] = i < STEM_PATCH_ELEMS ? ((uint32_t)((c * SI_ROWS + r) * SI_LD + col) << 16) | (c << 12) | (r << 6) | col : 0xffffffffu;
   }
+  // shared memory that is written once: zeroed weight tile (K padding), zero patch padding columns 37..39
+  for (int i = tid; i < STEM_N * SW_LD / 8; i += STEM_THREADS) reinterpret_cast<uint4*>(wsm)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 3 * SI_ROWS * (SI_LD - SI_COLS); i += STEM_THREADS)
+    patch[(i / (SI_LD - SI_COLS)) * SI_LD + SI_COLS + i % (SI_LD - SI_COLS)] = __float2bfloat16_rn(0.f);
+  __syncthreads();
   pdl_grid_sync();
-  for (int i = tid; i < STEM_N * (SKP / 8); i += STEM_THREADS) {
-    const int n = i / (SKP / 8), c8 = i - n * (SKP / 8);
-    *reinterpret_cast<uint4*>(wsm + n * SW_LD + c8 * 8) = *reinterpret_cast<const uint4*>(w + n * SKP + c8 * 8);
+  for (int i = tid; i < STEM_N * SK; i += STEM_THREADS) {
+    const int n = i / SK, k = i - n * SK;
+    const int c = k / 49, r = k - c * 49, ky = r / 7, kx = r - ky * 7;
+    wsm[n * SW_LD + (c * 7 + ky) * 8 + kx] = w[n * SK_IN + k];
   }
   if (tid < STEM_N) sbias[tid] = bias[tid];
 
   const int tiles_x = (Wp + SP_COLS - 1) / SP_COLS, tiles_y = (Hp + SP_ROWS - 1) / SP_ROWS;
   const int tiles = B * tiles_y * tiles_x;
-  const unsigned short* patch16 = reinterpret_cast<const unsigned short*>(patch);
+  const uint32_t* patch32 = reinterpret_cast<const uint32_t*>(patch);
   // The input patch of the NEXT tile is fetched into registers while the current tile computes (all loads of a thread in
   // flight together), and written to shared memory at the top of the next iteration.
   float pf[STEM_PF];
-  auto prefetch = [&](int tile) { stem_prefetch(pf, img, tile, tiles_x, tiles_y, H, W, tid); };
-  if (blockIdx.x < tiles) prefetch(blockIdx.x);
+  if (blockIdx.x < tiles) stem_prefetch(pf, pe, img, blockIdx.x, tiles_x, tiles_y, H, W);
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int b = tile / (tiles_y * tiles_x), tr = tile - b * tiles_y * tiles_x;
     const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
@@ -225,30 +236,22 @@ resnet_stem_tc_kernel(const float* __restrict__ img, const bf16* __restrict__ w,
     const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;              // first convolution pixel (halo row / column)
     __syncthreads();                                              // previous iteration's pooling has read `stage`; weights landed
 #pragma unroll
-    for (int j = 0; j < STEM_PF; ++j) {
-      const int i = tid + j * STEM_THREADS;
-      if (i < STEM_PATCH_ELEMS) {
-        const int c = i / (SI_ROWS * SI_COLS), r2 = i - c * (SI_ROWS * SI_COLS);
-        const int r = r2 / SI_COLS, col = r2 - r * SI_COLS;
-        patch[(c * SI_ROWS + r) * SI_LD + col] = __float2bfloat16_rn(pf[j]);
-      }
-    }
+    for (int j = 0; j < STEM_PF; ++j)
+      if (pe[j] != 0xffffffffu) patch[pe[j] >> 16] = __float2bfloat16_rn(pf[j]);
     __syncthreads();
-    if (tile + (int)gridDim.x < tiles) prefetch(tile + gridDim.x);
+    if (tile + (int)gridDim.x < tiles) stem_prefetch(pf, pe, img, tile + gridDim.x, tiles_x, tiles_y, H, W);
 
     // ---- convolution row `warp` of the tile: 16 pixels x 64 channels
+    if (warp < SC_ROWS) {
     float acc[STEM_N / 8][4];
 #pragma unroll
     for (int nt = 0; nt < STEM_N / 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-    const uint32_t base0 = (uint32_t)(2 * warp * SI_LD + 2 * g), base1 = base0 + 16;   // pixels g and g + 8 of the row
+    const uint32_t base0 = (uint32_t)(warp * SI_LD + g), base1 = base0 + 8;   // words: pixels g and g + 8 of the row
     const uint32_t wbase = smem_u32(wsm + ((lane >> 4) * 8 + (lane & 7)) * SW_LD + ((lane >> 3) & 1) * 8);
 #pragma unroll
     for (int ks = 0; ks < SKP / 16; ++ks) {
-      const uint32_t o0 = kp[ks][0] & 0xffffu, o1 = kp[ks][0] >> 16, o2 = kp[ks][1] & 0xffffu, o3 = kp[ks][1] >> 16;
-      const uint32_t a0 = patch16[base0 + o0] | ((uint32_t)patch16[base0 + o1] << 16);
-      const uint32_t a1 = patch16[base1 + o0] | ((uint32_t)patch16[base1 + o1] << 16);
-      const uint32_t a2 = patch16[base0 + o2] | ((uint32_t)patch16[base0 + o3] << 16);
-      const uint32_t a3 = patch16[base1 + o2] | ((uint32_t)patch16[base1 + o3] << 16);
+      const uint32_t o0 = kp[ks] & 0xffffu, o1 = kp[ks] >> 16;
+      const uint32_t a0 = patch32[base0 + o0], a1 = patch32[base1 + o0], a2 = patch32[base0 + o1], a3 = patch32[base1 + o1];
 #pragma unroll
       for (int np = 0; np < STEM_N / 16; ++np) {
         uint32_t b0, b1, b2, b3;   // (n-tile 2np: k lo, k hi), (n-tile 2np+1: k lo, k hi)
@@ -269,6 +272,7 @@ resnet_stem_tc_kernel(const float* __restrict__ img, const bf16* __restrict__ w,
       const uint32_t v1 = ok1 ? pack_bf16x2(fmaxf(acc[nt][2] + bb.x, 0.f), fmaxf(acc[nt][3] + bb.y, 0.f)) : 0u;
       *reinterpret_cast<uint32_t*>(srow + g * SO_LD + nt * 8 + 2 * t) = v0;
       *reinterpret_cast<uint32_t*>(srow + (g + 8) * SO_LD + nt * 8 + 2 * t) = v1;
+    }
     }
     __syncthreads();
     // ---- 3x3/2 max-pool over the parked rows: one (pooled pixel, 8-channel chunk) per thread
@@ -363,6 +367,9 @@ extern "C" int mvlt_resnet_stem_tc(const float* img, const void* w, const float*
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(resnet_stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    // two CTAs per SM
+    e = cudaFuncSetAttribute(resnet_stem_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }

@@ -7,9 +7,10 @@ from medical_vision_langauge_transformer_b200 import synth, runtime
 from medical_vision_langauge_transformer_b200.modules import config as C, model as M
 ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=64); ap.add_argument("--passes", type=int, default=2)
 ap.add_argument("--max-length", type=int, default=80); ap.add_argument("--count-only", action="store_true")
+ap.add_argument("--conv", default="swintransformer")
 a = ap.parse_args()
 torch.manual_seed(0)
-model = M.MVLBertForVQA(C.offline_config("vqa", max_length=a.max_length)).eval().cuda()
+model = M.MVLBertForVQA(C.offline_config("vqa", max_length=a.max_length, conv=a.conv)).eval().cuda()
 x, ids = synth.synth_images(a.batch, 1, 0.02).cuda(), synth.synth_token_ids(a.batch, a.max_length, 1).cuda()
 with torch.no_grad():
     if a.count_only:

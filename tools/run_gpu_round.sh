@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m gpu --timeout 600 2>&1 | tail -8 > gpurun_out/t_all.log
-timeout 300 python tools/step_timeline.py --conv resnet101 > gpurun_out/timeline_resnet101.log 2>&1
-tail -n 8 gpurun_out/t_all.log; head -n 14 gpurun_out/timeline_resnet101.log
+timeout 600 python -m pytest tests/test_resnet_gpu.py -q --timeout 300 -k "stem or golden" 2>&1 | tail -5 > gpurun_out/t_resnet.log
+ncu --set full --clock-control none --import-source on -k regex:resnet_stem -s 1 -c 1 -o gpurun_out/stem -f python tools/profile_step.py --conv resnet101 --passes 2 > gpurun_out/ncu_resnet.log 2>&1
+tail -n 3 gpurun_out/t_resnet.log

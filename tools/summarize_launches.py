@@ -1,5 +1,5 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum] --csv` launch list:
-keeps the LAST forward pass (from the last patch_embed_ln_kernel launch on) and prints per-kernel totals (time share,
+keeps the LAST forward pass (from the last patch_embed_ln / resnet_stem launch on) and prints per-kernel totals (time share,
 DRAM bytes when captured).  `--order` also lists the launches in order; `--traffic-json PATH` writes the mean DRAM
 bytes per gemm_tc launch (bench.py's roofline.traffic)."""
 import collections, csv, json, sys
@@ -19,7 +19,7 @@ for r in rows[hi + 1:]:
         scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(r[mu], 1)
         d[r[mn]] = v * scale
 L = list(launch.values())
-start = max(i for i, d in enumerate(L) if 'patch_embed_ln' in d['name'])
+start = max(i for i, d in enumerate(L) if 'patch_embed_ln' in d['name'] or 'resnet_stem' in d['name'])
 L = L[start:]
 tot = sum(d['us'] for d in L)
 agg = collections.OrderedDict()
