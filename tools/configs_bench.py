@@ -1,0 +1,82 @@
+"""Device-resident forward throughput of the other BASELINE.json configurations (the headline line is bench.py):
+  config2  SLAKE-shaped Med-VQA forward + classifier head, batch 64, L = 23, bf16          (configs[1] at its own length)
+  config3  RGC-shaped pretraining forward (MLM + ITM loss), batch 32 per GPU, L = 80        (configs[2]; both mask branches)
+  config5  ResNet-101 backbone variant + BERT-base, batch 64, L = 80                        (configs[4])
+Each forward is captured in a CUDA graph (runtime.GraphRunner) and replayed `--steps` times between two events with four
+rotated input batches; one JSON line per configuration.  python tools/configs_bench.py [--only config3]"""
+import argparse, json, os, random, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import torch
+from medical_vision_langauge_transformer_b200 import runtime, synth
+from medical_vision_langauge_transformer_b200.modules import config as C, model as M
+from oracle import mvlt_oracle as O   # FLOP accounting only
+
+ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=30); ap.add_argument("--warmup", type=int, default=5)
+ap.add_argument("--only", default="")
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+
+
+def timed(runner, batches, steps, warmup):
+    def run(k):
+        for i in range(k):
+            slot = i % 2
+            with torch.cuda.stream(runner.compute):
+                for dst, src in zip(runner.static_in[slot], batches[i % len(batches)]):
+                    dst.copy_(src, non_blocking=True)
+            runner.replay(slot)
+    run(warmup); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(runner.compute); run(steps); e1.record(runner.compute); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def emit(name, B, ms, launches, gflop_pair, extra=None):
+    d = {"config": name, "batch": B, "ms_per_step": ms, "pairs_per_s": B / ms * 1e3, "gpu_launches_per_step": launches,
+         "gflop_per_pair": gflop_pair, "achieved_tflops": B * gflop_pair / ms, "dtype": "bf16", "data": "synthetic, random init"}
+    d.update(extra or {})
+    print(json.dumps(d), flush=True)
+
+
+def vqa_like(name, conv, B, L):
+    torch.manual_seed(0)
+    model = M.MVLBertForVQA(C.offline_config("vqa", max_length=L, conv=conv)).eval().to(dev).set_precision("bf16")
+    batches = [(synth.synth_images(B, 200 + i, 0.02).to(dev), synth.synth_token_ids(B, L, 200 + i, min_len=min(10, L)).to(dev)) for i in range(4)]
+    runner = runtime.GraphRunner(lambda im, tx: model(im, tx, None), batches[0], slots=2)
+    ms = timed(runner, batches, a.steps, a.warmup)
+    flop = O.flops_per_pair(L, conv) - 2 * 768 * 768 + 2 * 768 * 224
+    emit(name, B, ms, runner.launches_per_replay, flop / 1e9, {"max_length": L, "conv": conv})
+
+
+def pretrain(B=32, L=80):
+    torch.manual_seed(0)
+    model = M.MVLBertForPretraining(C.offline_config("pretrain", max_length=L, ITM_task=True)).eval().to(dev).set_precision("bf16")
+    batches = []
+    for i in range(4):
+        ids = synth.synth_token_ids(B, L, 300 + i)
+        masked, labels = synth.synth_mlm_labels(ids, 300 + i)
+        itm = (torch.arange(B) % 2).long()
+        batches.append((synth.synth_images(B, 300 + i, 0.02).to(dev), masked.to(dev), labels.to(dev), itm.to(dev)))
+    for branch, seed in (("seq2seq", None), ("bidir", None)):
+        for s in range(64):                      # a Python seed whose first draw selects this branch (model.py:390-394)
+            random.seed(s)
+            if (random.random() < 0.5) == (branch == "seq2seq"):
+                seed = s
+                break
+
+        def fwd(im, tx, lab, itm, seed=seed):
+            random.seed(seed)
+            return model(im, tx, lab, itm)
+        runner = runtime.GraphRunner(fwd, batches[0], slots=2)
+        ms = timed(runner, batches, a.steps, a.warmup)
+        flop = O.flops_per_pair(L) - 2 * 768 * 768 + 2 * L * (768 * 768 + 768 * 30522) + 2 * 768 * 2
+        emit(f"config3 pretraining forward MLM+ITM ({branch} mask)", B, ms, runner.launches_per_replay, flop / 1e9,
+             {"max_length": L, "loss": float(runner.replay(0)[0].item())})
+
+
+if a.only in ("", "config2"):
+    vqa_like("config2 SLAKE-shaped VQA forward (Swin-S + BERT-base)", "swintransformer", 64, 23)
+if a.only in ("", "config3"):
+    pretrain()
+if a.only in ("", "config5"):
+    vqa_like("config5 ResNet-101 + BERT-base VQA forward", "resnet101", 64, 80)
