@@ -237,8 +237,11 @@ window_attn_warp_kernel(const WinParams p) {
 // ---- BERT joint attention, bf16: one CTA per (sample, head), one 16-row query tile per warp --------------------------
 // grid = (B, heads); block = 32 * NPAD/16.  Q/K/V rows are cp.async'ed into padded shared memory; the score
 // accumulators start from (additive key mask | seq2seq mask) / scale; exp2 with the scale folded in; P.V from registers.
-template <int NPAD>
-__global__ void __launch_bounds__(NPAD * 2, NPAD > 96 ? 2 : 3)
+// NWARPS warps per CTA, each walking the 16-row query tiles warp, warp + NWARPS, ...: three warps x three tiles for the
+// 131-token joint sequence.  (One warp per tile = 9 warps is allocated as 12 — warps come in fours — which capped the
+// kernel at 96 registers, 100 B of spills and ONE CTA per SM: ptxas -v / ncu launch__occupancy_limit_registers.)
+template <int NPAD, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, NPAD > 144 ? 2 : 3)
 joint_attn_kernel(const AttnParams p) {
   pdl_grid_sync();
   constexpr int HD = 64, LDS = HD + 8, NT = NPAD / 8, CPR = HD / 8;
@@ -253,20 +256,20 @@ joint_attn_kernel(const AttnParams p) {
   const bf16* qkv = reinterpret_cast<const bf16*>(p.qkv) + (long long)group * p.ntok * p.ld_qkv + head * HD;
   const float inv_scale = 1.0f / p.scale, c = p.scale * LOG2E;
 
-  for (int idx = tid; idx < NPAD * 3 * CPR; idx += NPAD * 2) {
+  for (int idx = tid; idx < NPAD * 3 * CPR; idx += NWARPS * 32) {
     const int ch = idx % CPR, which = (idx / CPR) % 3, i = idx / (3 * CPR);
     bf16* dst = Qs + which * (NPAD * LDS) + i * LDS + ch * 8;
     if (i < p.ntok) cp_async16(dst, qkv + (long long)i * p.ld_qkv + which * p.C + ch * 8);
     else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
   }
-  for (int i = tid; i < NPAD; i += NPAD * 2)
+  for (int i = tid; i < NPAD; i += NWARPS * 32)
     aux[i] = i < p.ntok ? (p.seq2seq ? 0.f : p.kmask[(long long)group * p.ntok + i] * inv_scale) : NEG_BIG;
   cp_async_wait_all();
   __syncthreads();
 
   const int g = lane >> 2, t = lane & 3;
-  const int r0 = warp * 16;
-  if (r0 >= p.ntok) return;
+  bf16* out = reinterpret_cast<bf16*>(p.out) + (long long)group * p.ntok * p.ld_out + head * HD;
+  for (int r0 = warp * 16; r0 < p.ntok; r0 += NWARPS * 16) {
   const int i0 = r0 + g, i1 = r0 + g + 8;
   float s[NT][4];
 #pragma unroll
@@ -341,12 +344,12 @@ joint_attn_kernel(const AttnParams p) {
     *reinterpret_cast<uint32_t*>(Qs + i1 * LDS + dn * 8 + 2 * t) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
   }
   __syncwarp();
-  bf16* out = reinterpret_cast<bf16*>(p.out) + (long long)group * p.ntok * p.ld_out + head * HD;
   for (int idx = lane; idx < 16 * CPR; idx += 32) {
     const int rr = idx / CPR, ch = idx % CPR;
     const int i = r0 + rr;
     if (i < p.ntok)
       *reinterpret_cast<uint4*>(out + (long long)i * p.ld_out + ch * 8) = *reinterpret_cast<const uint4*>(Qs + i * LDS + ch * 8);
+  }
   }
 }
 
@@ -428,6 +431,8 @@ static int set_smem(K kernel, int bytes) {
 
 constexpr int JOINT_NPAD = 144;   // 131 joint tokens (L=80) -> 9 query tiles; shorter L uses the same kernel
 constexpr int JOINT_NPAD_S = 96;  // S <= 96 (e.g. SLAKE L=23 -> 74, VQA-RAD L=30 -> 81)
+constexpr int JOINT_NPAD_L = 192; // two-image IU-Xray input (model.py:240-253): 98 image tokens, S = 100 + L <= 192
+constexpr int JOINT_WARPS = 3;    // 9 (6) query tiles = 3 (2) per warp
 
 }  // namespace mvlt
 
@@ -435,7 +440,8 @@ using namespace mvlt;
 
 extern "C" int mvlt_attn_init(void) {
   int rc;
-  if ((rc = set_smem(joint_attn_kernel<JOINT_NPAD>, 3 * JOINT_NPAD * 72 * 2 + JOINT_NPAD * 4)) != MVLT_OK) return rc;
+  if ((rc = set_smem(joint_attn_kernel<JOINT_NPAD, JOINT_WARPS>, 3 * JOINT_NPAD * 72 * 2 + JOINT_NPAD * 4)) != MVLT_OK) return rc;
+  if ((rc = set_smem(joint_attn_kernel<JOINT_NPAD_L, JOINT_WARPS>, 3 * JOINT_NPAD_L * 72 * 2 + JOINT_NPAD_L * 4)) != MVLT_OK) return rc;
   if ((rc = set_smem(window_attn_warp_kernel, WA_WARPS * WA_WARP_BYTES)) != MVLT_OK) return rc;
   if ((rc = set_smem(attn_f32_kernel<64, false>, 200 * 1024)) != MVLT_OK) return rc;
   if ((rc = set_smem(attn_f32_kernel<32, true>, 64 * 1024)) != MVLT_OK) return rc;
@@ -485,9 +491,11 @@ extern "C" int mvlt_joint_attention(const void* qkv, void* out, int dtype, const
   dim3 grid(B, heads);
   if (dtype == MVLT_BF16) {
     if (S <= JOINT_NPAD_S)
-      launch_k(joint_attn_kernel<JOINT_NPAD_S>, dim3(grid), dim3(JOINT_NPAD_S * 2), 3 * JOINT_NPAD_S * 72 * 2 + JOINT_NPAD_S * 4, stream, p);
+      launch_k(joint_attn_kernel<JOINT_NPAD_S, JOINT_WARPS>, dim3(grid), dim3(JOINT_WARPS * 32), 3 * JOINT_NPAD_S * 72 * 2 + JOINT_NPAD_S * 4, stream, p);
     else if (S <= JOINT_NPAD)
-      launch_k(joint_attn_kernel<JOINT_NPAD>, dim3(grid), dim3(JOINT_NPAD * 2), 3 * JOINT_NPAD * 72 * 2 + JOINT_NPAD * 4, stream, p);
+      launch_k(joint_attn_kernel<JOINT_NPAD, JOINT_WARPS>, dim3(grid), dim3(JOINT_WARPS * 32), 3 * JOINT_NPAD * 72 * 2 + JOINT_NPAD * 4, stream, p);
+    else if (S <= JOINT_NPAD_L)
+      launch_k(joint_attn_kernel<JOINT_NPAD_L, JOINT_WARPS>, dim3(grid), dim3(JOINT_WARPS * 32), 3 * JOINT_NPAD_L * 72 * 2 + JOINT_NPAD_L * 4, stream, p);
     else return MVLT_ERR_UNSUPPORTED;
   } else if (dtype == MVLT_F32) {
     const int npad = (S + 3) & ~3;

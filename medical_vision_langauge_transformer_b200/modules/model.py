@@ -273,7 +273,11 @@ class Conv_layer(nn.Module):
 
     def forward(self, v):
         if torch.is_tensor(v) and v.dim() == 5:
-            raise NotImplementedError("5-D two-image IU-Xray input (model.py:240-253) is outside the accelerated path")
+            # IU-Xray: [batch, 2, channel, h, w] -> the two views' objects concatenated, [batch, 2*49, hidden] (model.py:240-253,
+            # then resnet_fc per object, :263-264).  Both views go through the backbone as ONE batch of 2B images.
+            B = v.shape[0]
+            obj = self.forward(v.transpose(0, 1).reshape(2 * B, *v.shape[2:]))            # [2B, 49, D], view-major
+            return torch.cat((obj[:B], obj[B:]), dim=1)
         backbone = self.conv[0]
         if isinstance(backbone, SwinTransformer):
             return backbone.forward_features(v, final_gelu=True, out_dtype=torch.float32)

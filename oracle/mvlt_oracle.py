@@ -187,6 +187,8 @@ def conv_layer(sd: SD, img: Tensor, taps: Optional[dict] = None) -> Tensor:
     """model.py:232-235,255-266 — Sequential(backbone, GELU); 4-D branch.  Swin: feature dim 768 so no resnet_fc.
     ResNet (keys `conv.conv.0.layer1...`): [B,2048,7,7] -> reshape/transpose [B,49,2048] (:258-261) -> resnet_fc (:263-264);
     the depth is read off the state_dict (layer3 has 23 blocks for resnet101, 6 for resnet50)."""
+    if img.dim() == 5:                       # IU-Xray two-view input, model.py:240-253: objects of both views concatenated
+        return torch.cat((conv_layer(sd, img[:, 0], taps), conv_layer(sd, img[:, 1])), dim=1)
     if "conv.conv.0.layer1.0.conv1.weight" in sd:
         layers = tuple(sum(1 for k in sd if k.startswith(f"conv.conv.0.layer{i}.") and k.endswith(".conv1.weight"))
                        for i in (1, 2, 3, 4))

@@ -120,3 +120,6 @@ def test_oracle_vs_live_reference():
     x, ids = synth.synth_images(2, 21, 1.0), synth.synth_token_ids(2, 80, 21)
     with torch.no_grad():
         assert torch.allclose(m(x, ids), O.retrieval_forward(sd, x, ids), atol=1e-6)
+        # IU-Xray two-view input [B, 2, 3, H, W] (model.py:240-253): 98 image tokens
+        x5 = synth.synth_images(2, 22, 1.0).view(1, 2, 3, 224, 224)
+        assert torch.allclose(m(x5, ids[:1]), O.retrieval_forward(sd, x5, ids[:1]), atol=1e-6)

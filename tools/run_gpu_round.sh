@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python tools/configs_bench.py > gpurun_out/configs_bench.jsonl 2> gpurun_out/configs_bench.err
-cat gpurun_out/configs_bench.jsonl | cut -c1-330; tail -n 3 gpurun_out/configs_bench.err
+timeout 900 python -m pytest tests -q -m gpu --timeout 600 2>&1 | tail -12 > gpurun_out/t_all.log
+tail -n 12 gpurun_out/t_all.log
