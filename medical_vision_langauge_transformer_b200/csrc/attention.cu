@@ -11,6 +11,8 @@
 // bf16 path: one CTA per (group, head); Q/K/V rows staged in padded smem with 16 B loads, S and P.V on the tensor
 // cores (mma.sync m16n8k16, fp32 accumulate) with the whole score row in registers — S/P never touch HBM.
 // fp32 path ("parity mode"): same indexing, CUDA-core arithmetic.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mvlt {
@@ -27,6 +29,7 @@ struct AttnParams {
   // joint mode
   const float* kmask;    // [B, ntok]
   int seq2seq, obj_end;
+  int head_major;        // joint mode: blockIdx.x = head (the 12 heads of a sample run together: whole qkv rows stay hot)
 };
 
 template <bool WINDOW>
@@ -234,122 +237,152 @@ window_attn_warp_kernel(const WinParams p) {
   }
 }
 
-// ---- BERT joint attention, bf16: one CTA per (sample, head), one 16-row query tile per warp --------------------------
-// grid = (B, heads); block = 32 * NPAD/16.  Q/K/V rows are cp.async'ed into padded shared memory; the score
+// ---- BERT joint attention, bf16: one CTA per (sample, head), key-chunked online softmax ----------------------------------
+// grid = (heads, B): the twelve heads of a sample are scheduled together.  Three warps per CTA, each walking the 16-row query
+// tiles warp, warp + 3, ...; the keys are walked in chunks of 48 with a running (max, sum) per row — 24 score registers
+// instead of the 72 of a full 144-key row; K / V live in UNPADDED, XOR-swizzled 128-byte rows, each query tile is staged in a
+// per-warp 2 KB buffer that is reused for the output: 43.6 KB and 128 registers, four to five CTAs per SM.  The score
 // accumulators start from (additive key mask | seq2seq mask) / scale; exp2 with the scale folded in; P.V from registers.
-// NWARPS warps per CTA, each walking the 16-row query tiles warp, warp + NWARPS, ...: three warps x three tiles for the
-// 131-token joint sequence.  (One warp per tile = 9 warps is allocated as 12 — warps come in fours — which capped the
-// kernel at 96 registers, 100 B of spills and ONE CTA per SM: ptxas -v / ncu launch__occupancy_limit_registers.)
-template <int NPAD, int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32, NPAD > 144 ? 2 : 3)
-joint_attn_kernel(const AttnParams p) {
+// History (ncu, profiles/r01_ncu_joint_attention_variants.txt): one warp per tile with full rows (9 warps allocated as 12,
+// 96-register cap, 100 B of spills, ONE CTA per SM), then 3 warps x 3 tiles with full rows (168 registers, 3 CTAs), then this
+// one all run 29-31 us for 768 (sample, head) items: every CTA of the single wave loads, then computes, in lock-step, so
+// the kernel is the SUM of its load phase and its mma.sync phase whatever the occupancy; a persistent, double-buffered item
+// loop is what would overlap them.
+// (launch bound of 128 threads although 96 run: warps are allocated in fours, so the register cap must be computed for four)
+template <int NCH>
+__global__ void __launch_bounds__(128, NCH <= 3 ? 4 : 3)
+joint_attn_flash_kernel(const AttnParams p) {
   pdl_grid_sync();
-  constexpr int HD = 64, LDS = HD + 8, NT = NPAD / 8, CPR = HD / 8;
+  constexpr int HD = 64, KEYS = 48 * NCH, NW = 3, CPR = HD / 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
-  bf16* Qs = reinterpret_cast<bf16*>(smem_attn);
-  bf16* Ks = Qs + NPAD * LDS;
-  bf16* Vs = Ks + NPAD * LDS;
-  float* aux = reinterpret_cast<float*>(Vs + NPAD * LDS);  // [NPAD] additive key mask / scale (NEG_BIG beyond ntok)
-
-  const int group = blockIdx.x, head = blockIdx.y;
+  bf16* Ks = reinterpret_cast<bf16*>(smem_attn);
+  bf16* Vs = Ks + KEYS * HD;
+  bf16* Qall = Vs + KEYS * HD;
+  float* aux = reinterpret_cast<float*>(Qall + NW * 16 * HD);  // [KEYS] additive key mask / scale (NEG_BIG beyond ntok)
+  const int group = p.head_major ? blockIdx.y : blockIdx.x, head = p.head_major ? blockIdx.x : blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  bf16* Qw = Qall + warp * 16 * HD;
   const bf16* qkv = reinterpret_cast<const bf16*>(p.qkv) + (long long)group * p.ntok * p.ld_qkv + head * HD;
   const float inv_scale = 1.0f / p.scale, c = p.scale * LOG2E;
+  // element offset of 16-byte chunk `ch` of row `row` in a swizzled [rows][64] bf16 tile
+  auto swz = [](int row, int ch) { return row * HD + ((ch ^ (row & 7)) << 3); };
 
-  for (int idx = tid; idx < NPAD * 3 * CPR; idx += NWARPS * 32) {
-    const int ch = idx % CPR, which = (idx / CPR) % 3, i = idx / (3 * CPR);
-    bf16* dst = Qs + which * (NPAD * LDS) + i * LDS + ch * 8;
-    if (i < p.ntok) cp_async16(dst, qkv + (long long)i * p.ld_qkv + which * p.C + ch * 8);
+  for (int idx = tid; idx < KEYS * 2 * CPR; idx += NW * 32) {
+    const int ch = idx % CPR, which = (idx / CPR) & 1, i = idx / (2 * CPR);
+    bf16* dst = (which ? Vs : Ks) + swz(i, ch);
+    if (i < p.ntok) cp_async16(dst, qkv + (long long)i * p.ld_qkv + (1 + which) * p.C + ch * 8);
     else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
   }
-  for (int i = tid; i < NPAD; i += NWARPS * 32)
+  for (int i = tid; i < KEYS; i += NW * 32)
     aux[i] = i < p.ntok ? (p.seq2seq ? 0.f : p.kmask[(long long)group * p.ntok + i] * inv_scale) : NEG_BIG;
   cp_async_wait_all();
   __syncthreads();
 
   const int g = lane >> 2, t = lane & 3;
   bf16* out = reinterpret_cast<bf16*>(p.out) + (long long)group * p.ntok * p.ld_out + head * HD;
-  for (int r0 = warp * 16; r0 < p.ntok; r0 += NWARPS * 16) {
-  const int i0 = r0 + g, i1 = r0 + g + 8;
-  float s[NT][4];
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    const int j = nt * 8 + 2 * t;
-    const float2 m = *reinterpret_cast<const float2*>(aux + j);
-    s[nt][0] = s[nt][2] = m.x;
-    s[nt][1] = s[nt][3] = m.y;
-    if (p.seq2seq) {  // model.py:118-123: text rows see the image block and the text up to themselves
-      const float blocked = -10000.f * inv_scale;
-      if (j > i0 && j > p.obj_end) s[nt][0] += blocked;
-      if (j + 1 > i0 && j + 1 > p.obj_end) s[nt][1] += blocked;
-      if (j > i1 && j > p.obj_end) s[nt][2] += blocked;
-      if (j + 1 > i1 && j + 1 > p.obj_end) s[nt][3] += blocked;
+  for (int r0 = warp * 16; r0 < p.ntok; r0 += NW * 16) {
+    // ---- this warp's query tile -> Qw
+    for (int idx = lane; idx < 16 * CPR; idx += 32) {
+      const int rr = idx / CPR, ch = idx % CPR;
+      bf16* dst = Qw + swz(rr, ch);
+      if (r0 + rr < p.ntok) cp_async16(dst, qkv + (long long)(r0 + rr) * p.ld_qkv + ch * 8);
+      else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
     }
-  }
+    cp_async_wait_all();
+    __syncwarp();
+    uint32_t qa[4][4];
 #pragma unroll
-  for (int kq = 0; kq < HD / 32; ++kq) {
-    uint32_t qa[2][4];
+    for (int ks = 0; ks < 4; ++ks)
+      ldsm_x4(smem_u32(Qw + swz(lane & 15, ks * 2 + (lane >> 4))), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+    const int i0 = r0 + g, i1 = r0 + g + 8;
+    float o[HD / 8][4];
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks)
-      ldsm_x4(smem_u32(Qs + (r0 + (lane & 15)) * LDS + kq * 32 + ks * 16 + (lane >> 4) * 8), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+    for (int dn = 0; dn < HD / 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+    float m0 = NEG_BIG, m1 = NEG_BIG, l0 = 0.f, l1 = 0.f;   // running row max (score units) and this thread's partial row sums
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      uint32_t b0, b1, b2, b3;
-      ldsm_x4(smem_u32(Ks + (nt * 8 + (lane & 7)) * LDS + kq * 32 + (lane >> 3) * 8), b0, b1, b2, b3);
-      mma_bf16_16816(s[nt], qa[0][0], qa[0][1], qa[0][2], qa[0][3], b0, b1);
-      mma_bf16_16816(s[nt], qa[1][0], qa[1][1], qa[1][2], qa[1][3], b2, b3);
+    for (int chn = 0; chn < NCH; ++chn) {
+      const int k0 = chn * 48;
+      if (k0 < p.ntok) {   // warp-uniform; a chunk entirely beyond the sequence contributes nothing
+        float s[6][4];
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) {
+          const int j = k0 + nt * 8 + 2 * t;
+          const float2 m = *reinterpret_cast<const float2*>(aux + j);
+          s[nt][0] = s[nt][2] = m.x;
+          s[nt][1] = s[nt][3] = m.y;
+          if (p.seq2seq) {  // model.py:118-123: text rows see the image block and the text up to themselves
+            const float blocked = -10000.f * inv_scale;
+            if (j > i0 && j > p.obj_end) s[nt][0] += blocked;
+            if (j + 1 > i0 && j + 1 > p.obj_end) s[nt][1] += blocked;
+            if (j > i1 && j > p.obj_end) s[nt][2] += blocked;
+            if (j + 1 > i1 && j + 1 > p.obj_end) s[nt][3] += blocked;
+          }
+        }
+#pragma unroll
+        for (int kq = 0; kq < 2; ++kq)
+#pragma unroll
+          for (int nt = 0; nt < 6; ++nt) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(smem_u32(Ks + swz(k0 + nt * 8 + (lane & 7), kq * 4 + (lane >> 3))), b0, b1, b2, b3);
+            mma_bf16_16816(s[nt], qa[2 * kq][0], qa[2 * kq][1], qa[2 * kq][2], qa[2 * kq][3], b0, b1);
+            mma_bf16_16816(s[nt], qa[2 * kq + 1][0], qa[2 * kq + 1][1], qa[2 * kq + 1][2], qa[2 * kq + 1][3], b2, b3);
+          }
+        float mx0 = s[0][0], mx1 = s[0][2];
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) {
+          mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+          mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float n0 = fmaxf(m0, mx0), n1 = fmaxf(m1, mx1);
+        const float corr0 = ex2_approx((m0 - n0) * c), corr1 = ex2_approx((m1 - n1) * c);
+        m0 = n0; m1 = n1;
+        const float m0c = -n0 * c, m1c = -n1 * c;
+        float sum0 = 0.f, sum1 = 0.f;
+        uint32_t pk[6][2];  // P as bf16 pairs: [nt][0] = row g, [nt][1] = row g+8
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) {
+          const float p0 = ex2_approx(fmaf(s[nt][0], c, m0c)), p1 = ex2_approx(fmaf(s[nt][1], c, m0c));
+          const float p2 = ex2_approx(fmaf(s[nt][2], c, m1c)), p3 = ex2_approx(fmaf(s[nt][3], c, m1c));
+          sum0 += p0 + p1;
+          sum1 += p2 + p3;
+          pk[nt][0] = pack_bf16x2(p0, p1);
+          pk[nt][1] = pack_bf16x2(p2, p3);
+        }
+        l0 = fmaf(l0, corr0, sum0);
+        l1 = fmaf(l1, corr1, sum1);
+        if (chn > 0) {
+#pragma unroll
+          for (int dn = 0; dn < HD / 8; ++dn) { o[dn][0] *= corr0; o[dn][1] *= corr0; o[dn][2] *= corr1; o[dn][3] *= corr1; }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+          for (int dp = 0; dp < HD / 16; ++dp) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4_t(smem_u32(Vs + swz(k0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, dp * 2 + (lane >> 4))), b0, b1, b2, b3);
+            mma_bf16_16816(o[2 * dp], pk[2 * kk][0], pk[2 * kk][1], pk[2 * kk + 1][0], pk[2 * kk + 1][1], b0, b1);
+            mma_bf16_16816(o[2 * dp + 1], pk[2 * kk][0], pk[2 * kk][1], pk[2 * kk + 1][0], pk[2 * kk + 1][1], b2, b3);
+          }
+      }
     }
-  }
-  float mx0 = s[0][0], mx1 = s[0][2];
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    __syncwarp();   // every lane has read its Q fragments: Qw becomes the output staging tile
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-    mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-  }
-  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-  const float m0c = -mx0 * c, m1c = -mx1 * c;
-  float sum0 = 0.f, sum1 = 0.f;
-  uint32_t pk[NT][2];  // P as bf16 pairs: [nt][0] = row g, [nt][1] = row g+8
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    const float p0 = ex2_approx(fmaf(s[nt][0], c, m0c)), p1 = ex2_approx(fmaf(s[nt][1], c, m0c));
-    const float p2 = ex2_approx(fmaf(s[nt][2], c, m1c)), p3 = ex2_approx(fmaf(s[nt][3], c, m1c));
-    sum0 += p0 + p1;
-    sum1 += p2 + p3;
-    pk[nt][0] = pack_bf16x2(p0, p1);
-    pk[nt][1] = pack_bf16x2(p2, p3);
-  }
-  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-
-  float o[HD / 8][4];
-#pragma unroll
-  for (int dn = 0; dn < HD / 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
-#pragma unroll
-  for (int kk = 0; kk < NPAD / 16; ++kk) {
-#pragma unroll
-    for (int dp = 0; dp < HD / 16; ++dp) {
-      uint32_t b0, b1, b2, b3;
-      ldsm_x4_t(smem_u32(Vs + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + dp * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
-      mma_bf16_16816(o[2 * dp], pk[2 * kk][0], pk[2 * kk][1], pk[2 * kk + 1][0], pk[2 * kk + 1][1], b0, b1);
-      mma_bf16_16816(o[2 * dp + 1], pk[2 * kk][0], pk[2 * kk][1], pk[2 * kk + 1][0], pk[2 * kk + 1][1], b2, b3);
+    for (int dn = 0; dn < HD / 8; ++dn) {
+      *reinterpret_cast<uint32_t*>(Qw + swz(g, dn) + 2 * t) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
+      *reinterpret_cast<uint32_t*>(Qw + swz(g + 8, dn) + 2 * t) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
     }
-  }
-  const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
-  __syncwarp();
-#pragma unroll
-  for (int dn = 0; dn < HD / 8; ++dn) {
-    *reinterpret_cast<uint32_t*>(Qs + i0 * LDS + dn * 8 + 2 * t) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
-    *reinterpret_cast<uint32_t*>(Qs + i1 * LDS + dn * 8 + 2 * t) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
-  }
-  __syncwarp();
-  for (int idx = lane; idx < 16 * CPR; idx += 32) {
-    const int rr = idx / CPR, ch = idx % CPR;
-    const int i = r0 + rr;
-    if (i < p.ntok)
-      *reinterpret_cast<uint4*>(out + (long long)i * p.ld_out + ch * 8) = *reinterpret_cast<const uint4*>(Qs + i * LDS + ch * 8);
-  }
+    __syncwarp();
+    for (int idx = lane; idx < 16 * CPR; idx += 32) {
+      const int rr = idx / CPR, ch = idx % CPR;
+      if (r0 + rr < p.ntok)
+        *reinterpret_cast<uint4*>(out + (long long)(r0 + rr) * p.ld_out + ch * 8) = *reinterpret_cast<const uint4*>(Qw + swz(rr, ch));
+    }
+    __syncwarp();   // the staging tile is free for the next query tile
   }
 }
 
@@ -429,19 +462,18 @@ static int set_smem(K kernel, int bytes) {
   return MVLT_OK;
 }
 
-constexpr int JOINT_NPAD = 144;   // 131 joint tokens (L=80) -> 9 query tiles; shorter L uses the same kernel
-constexpr int JOINT_NPAD_S = 96;  // S <= 96 (e.g. SLAKE L=23 -> 74, VQA-RAD L=30 -> 81)
-constexpr int JOINT_NPAD_L = 192; // two-image IU-Xray input (model.py:240-253): 98 image tokens, S = 100 + L <= 192
-constexpr int JOINT_WARPS = 3;    // 9 (6) query tiles = 3 (2) per warp
 
 }  // namespace mvlt
 
 using namespace mvlt;
 
+template <int NCH> constexpr int joint_flash_smem() { return 48 * NCH * 64 * 2 * 2 + 3 * 16 * 64 * 2 + 48 * NCH * 4; }
+
 extern "C" int mvlt_attn_init(void) {
   int rc;
-  if ((rc = set_smem(joint_attn_kernel<JOINT_NPAD, JOINT_WARPS>, 3 * JOINT_NPAD * 72 * 2 + JOINT_NPAD * 4)) != MVLT_OK) return rc;
-  if ((rc = set_smem(joint_attn_kernel<JOINT_NPAD_L, JOINT_WARPS>, 3 * JOINT_NPAD_L * 72 * 2 + JOINT_NPAD_L * 4)) != MVLT_OK) return rc;
+  if ((rc = set_smem(joint_attn_flash_kernel<2>, joint_flash_smem<2>())) != MVLT_OK) return rc;
+  if ((rc = set_smem(joint_attn_flash_kernel<3>, joint_flash_smem<3>())) != MVLT_OK) return rc;
+  if ((rc = set_smem(joint_attn_flash_kernel<4>, joint_flash_smem<4>())) != MVLT_OK) return rc;
   if ((rc = set_smem(window_attn_warp_kernel, WA_WARPS * WA_WARP_BYTES)) != MVLT_OK) return rc;
   if ((rc = set_smem(attn_f32_kernel<64, false>, 200 * 1024)) != MVLT_OK) return rc;
   if ((rc = set_smem(attn_f32_kernel<32, true>, 64 * 1024)) != MVLT_OK) return rc;
@@ -490,12 +522,14 @@ extern "C" int mvlt_joint_attention(const void* qkv, void* out, int dtype, const
   p.kmask = kmask; p.seq2seq = seq2seq; p.obj_end = obj_end;
   dim3 grid(B, heads);
   if (dtype == MVLT_BF16) {
-    if (S <= JOINT_NPAD_S)
-      launch_k(joint_attn_kernel<JOINT_NPAD_S, JOINT_WARPS>, dim3(grid), dim3(JOINT_WARPS * 32), 3 * JOINT_NPAD_S * 72 * 2 + JOINT_NPAD_S * 4, stream, p);
-    else if (S <= JOINT_NPAD)
-      launch_k(joint_attn_kernel<JOINT_NPAD, JOINT_WARPS>, dim3(grid), dim3(JOINT_WARPS * 32), 3 * JOINT_NPAD * 72 * 2 + JOINT_NPAD * 4, stream, p);
-    else if (S <= JOINT_NPAD_L)
-      launch_k(joint_attn_kernel<JOINT_NPAD_L, JOINT_WARPS>, dim3(grid), dim3(JOINT_WARPS * 32), 3 * JOINT_NPAD_L * 72 * 2 + JOINT_NPAD_L * 4, stream, p);
+    if (B > 65535) return MVLT_ERR_UNSUPPORTED;
+    p.head_major = 1;
+    grid = dim3(heads, B);
+  }
+  if (dtype == MVLT_BF16) {
+    if (S <= 96) launch_k(joint_attn_flash_kernel<2>, dim3(grid), dim3(96), joint_flash_smem<2>(), stream, p);
+    else if (S <= 144) launch_k(joint_attn_flash_kernel<3>, dim3(grid), dim3(96), joint_flash_smem<3>(), stream, p);
+    else if (S <= 192) launch_k(joint_attn_flash_kernel<4>, dim3(grid), dim3(96), joint_flash_smem<4>(), stream, p);
     else return MVLT_ERR_UNSUPPORTED;
   } else if (dtype == MVLT_F32) {
     const int npad = (S + 3) & ~3;
