@@ -140,8 +140,15 @@ int mvlt_joint_embed(const void* feat, int feat_dtype, const int* img_index, con
                      const float* typepos, void* out, int out_dtype, void* out_bf16_copy, float* kmask, int B, int n_obj,
                      int L, int D, int cls_id, int sep_id, mvlt_stream_t stream);
 
+/* ViT token assembly (torchvision vision_transformer.py `_process_input` + class token + pos_embedding, vfe.py:94-107):
+ * out fp32 [B, 1 + n_patch, D]; out[b,0] = cls + pos[0]; out[b,1+i] = patches[b*n_patch + i] + pos[1+i]. */
+int mvlt_vit_embed(const float* patches, const float* cls, const float* pos, float* out, int B, int n_patch, int D,
+                   mvlt_stream_t stream);
+
 /* BERT self-attention over the joint sequence: qkv [B*S, 3*heads*64] -> out [B*S, heads*64].
- * HF modeling_bert.py:115-140; seq2seq != 0 applies the mask of model.py:118-123 instead of kmask. */
+ * HF modeling_bert.py:115-140; seq2seq != 0 applies the mask of model.py:118-123 instead of kmask.  S <= 288 in bf16 (131 for
+ * Swin / ResNet features at L = 80, 180 for the two-view input, 197 inside the ViT trunk, 278 for ViT / linear-patch
+ * features); the same kernel is the nn.MultiheadAttention of the ViT encoder blocks (kmask = 0). */
 int mvlt_joint_attention(const void* qkv, void* out, int dtype, const float* kmask, int B, int S, int heads,
                          int head_dim, int seq2seq, int obj_end, float scale, mvlt_stream_t stream);
 

@@ -31,6 +31,7 @@ PROTOTYPES = {
     "mvlt_patch_merge_ln": [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "mvlt_window_attention": [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
     "mvlt_joint_embed": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "mvlt_vit_embed": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "mvlt_joint_attention": [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _f, _vp],
     "mvlt_linear_small": [_vp, _i, _ll, _vp, _vp, _vp, _ll, _i, _i, _vp],
     "mvlt_softmax_rows": [_vp, _vp, _ll, _i, _vp],

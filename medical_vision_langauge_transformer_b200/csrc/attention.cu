@@ -250,7 +250,7 @@ window_attn_warp_kernel(const WinParams p) {
 // loop is what would overlap them.
 // (launch bound of 128 threads although 96 run: warps are allocated in fours, so the register cap must be computed for four)
 template <int NCH>
-__global__ void __launch_bounds__(128, NCH <= 3 ? 4 : 3)
+__global__ void __launch_bounds__(128, NCH <= 3 ? 4 : (NCH == 4 ? 3 : 2))
 joint_attn_flash_kernel(const AttnParams p) {
   pdl_grid_sync();
   constexpr int HD = 64, KEYS = 48 * NCH, NW = 3, CPR = HD / 8;
@@ -387,49 +387,56 @@ joint_attn_flash_kernel(const AttnParams p) {
 }
 
 // ---- fp32 parity path: CUDA cores, scores in smem -------------------------------------------------------------------
+// Query rows are processed in blocks of `rb` (gridDim.z blocks per (group, head)): K / V of the whole sequence plus the
+// scores of one block live in shared memory, so joint sequences up to ~300 tokens (ViT / linear-patch backbones) fit.
 template <int HD, bool WINDOW>
 __global__ void __launch_bounds__(256)
-attn_f32_kernel(const AttnParams p, int npad) {
+attn_f32_kernel(const AttnParams p, int npad, int rb) {
   pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int N = p.ntok;
   constexpr int LD = HD + 1;
-  float* Qs = reinterpret_cast<float*>(smem_attn);
-  float* Ks = Qs + npad * LD;
+  float* Qs = reinterpret_cast<float*>(smem_attn);   // [rb][LD]
+  float* Ks = Qs + rb * LD;                           // [npad][LD]
   float* Vs = Ks + npad * LD;
   float* aux = Vs + npad * LD;
-  float* S = aux + npad;  // [N][npad+1]
+  float* S = aux + npad;  // [rb][npad+1]
   const int lds = npad + 1;
   const int group = blockIdx.x, head = blockIdx.y, tid = threadIdx.x;
+  const int row0 = blockIdx.z * rb, nr = min(rb, N - row0);
   const float* qkv = reinterpret_cast<const float*>(p.qkv);
-  for (int idx = tid; idx < N * 3 * HD; idx += blockDim.x) {
-    const int d = idx % HD, which = (idx / HD) % 3, i = idx / (3 * HD);
+  for (int idx = tid; idx < N * 2 * HD; idx += blockDim.x) {
+    const int d = idx % HD, which = (idx / HD) % 2, i = idx / (2 * HD);
     const long long row = token_row<WINDOW>(p, group, i);
-    (which == 0 ? Qs : which == 1 ? Ks : Vs)[i * LD + d] = qkv[row * p.ld_qkv + which * p.C + head * HD + d];
+    (which == 0 ? Ks : Vs)[i * LD + d] = qkv[row * p.ld_qkv + (1 + which) * p.C + head * HD + d];
+  }
+  for (int idx = tid; idx < nr * HD; idx += blockDim.x) {
+    const int d = idx % HD, i = idx / HD;
+    Qs[i * LD + d] = qkv[token_row<WINDOW>(p, group, row0 + i) * p.ld_qkv + head * HD + d];
   }
   for (int i = tid; i < N; i += blockDim.x)
     aux[i] = WINDOW ? (p.shift > 0 ? (float)shift_region(p, group, i) : 0.f) : p.kmask[(long long)group * N + i];
   __syncthreads();
-  for (int idx = tid; idx < N * N; idx += blockDim.x) {
-    const int i = idx / N, j = idx % N;
+  for (int idx = tid; idx < nr * N; idx += blockDim.x) {
+    const int il = idx / N, j = idx % N, i = row0 + il;
     float acc = 0.f;
     if (WINDOW) {
       // reference scales q before the product (vfe.py:234)
 #pragma unroll
-      for (int d = 0; d < HD; ++d) acc = fmaf(Qs[i * LD + d] * p.scale, Ks[j * LD + d], acc);
+      for (int d = 0; d < HD; ++d) acc = fmaf(Qs[il * LD + d] * p.scale, Ks[j * LD + d], acc);
       acc += p.relbias[((long long)head * 64 + i) * 64 + j];
       if (aux[i] != aux[j]) acc += -100.f;
     } else {
 #pragma unroll
-      for (int d = 0; d < HD; ++d) acc = fmaf(Qs[i * LD + d], Ks[j * LD + d], acc);
+      for (int d = 0; d < HD; ++d) acc = fmaf(Qs[il * LD + d], Ks[j * LD + d], acc);
       acc *= p.scale;
       acc += p.seq2seq ? ((j <= i || j <= p.obj_end) ? 0.f : -10000.f) : aux[j];
     }
-    S[i * lds + j] = acc;
+    S[il * lds + j] = acc;
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-  for (int i = warp; i < N; i += nwarps) {
+  for (int i = warp; i < nr; i += nwarps) {
     float mx = -INFINITY;
     for (int j = lane; j < N; j += 32) mx = fmaxf(mx, S[i * lds + j]);
     mx = warp_max(mx);
@@ -445,13 +452,14 @@ attn_f32_kernel(const AttnParams p, int npad) {
   }
   __syncthreads();
   float* out = reinterpret_cast<float*>(p.out);
-  for (int idx = tid; idx < N * HD; idx += blockDim.x) {
+  for (int idx = tid; idx < nr * HD; idx += blockDim.x) {
     const int i = idx / HD, d = idx % HD;
     float acc = 0.f;
     for (int j = 0; j < N; ++j) acc = fmaf(S[i * lds + j], Vs[j * LD + d], acc);
-    out[token_row<WINDOW>(p, group, i) * p.ld_out + head * HD + d] = acc;
+    out[token_row<WINDOW>(p, group, row0 + i) * p.ld_out + head * HD + d] = acc;
   }
 }
+
 
 template <typename K>
 static int set_smem(K kernel, int bytes) {
@@ -474,6 +482,8 @@ extern "C" int mvlt_attn_init(void) {
   if ((rc = set_smem(joint_attn_flash_kernel<2>, joint_flash_smem<2>())) != MVLT_OK) return rc;
   if ((rc = set_smem(joint_attn_flash_kernel<3>, joint_flash_smem<3>())) != MVLT_OK) return rc;
   if ((rc = set_smem(joint_attn_flash_kernel<4>, joint_flash_smem<4>())) != MVLT_OK) return rc;
+  if ((rc = set_smem(joint_attn_flash_kernel<5>, joint_flash_smem<5>())) != MVLT_OK) return rc;
+  if ((rc = set_smem(joint_attn_flash_kernel<6>, joint_flash_smem<6>())) != MVLT_OK) return rc;
   if ((rc = set_smem(window_attn_warp_kernel, WA_WARPS * WA_WARP_BYTES)) != MVLT_OK) return rc;
   if ((rc = set_smem(attn_f32_kernel<64, false>, 200 * 1024)) != MVLT_OK) return rc;
   if ((rc = set_smem(attn_f32_kernel<32, true>, 64 * 1024)) != MVLT_OK) return rc;
@@ -504,8 +514,8 @@ extern "C" int mvlt_window_attention(const void* qkv, void* out, int dtype, cons
     launch_k(window_attn_warp_kernel, dim3(gridx), dim3(WA_WARPS * 32), WA_WARPS * WA_WARP_BYTES, stream, wp);
   } else if (dtype == MVLT_F32) {
     const int npad = 52;
-    const int bytes = (3 * npad * 33 + npad + 49 * (npad + 1)) * 4;
-    launch_k(attn_f32_kernel<32, true>, dim3(grid), dim3(128), bytes, stream, p, npad);
+    const int bytes = (49 * 33 + 2 * npad * 33 + npad + 49 * (npad + 1)) * 4;
+    launch_k(attn_f32_kernel<32, true>, dim3(grid), dim3(128), bytes, stream, p, npad, 49);
   } else return MVLT_ERR_INVALID;
   MVLT_LAUNCH_CHECK();
   return MVLT_OK;
@@ -530,12 +540,16 @@ extern "C" int mvlt_joint_attention(const void* qkv, void* out, int dtype, const
     if (S <= 96) launch_k(joint_attn_flash_kernel<2>, dim3(grid), dim3(96), joint_flash_smem<2>(), stream, p);
     else if (S <= 144) launch_k(joint_attn_flash_kernel<3>, dim3(grid), dim3(96), joint_flash_smem<3>(), stream, p);
     else if (S <= 192) launch_k(joint_attn_flash_kernel<4>, dim3(grid), dim3(96), joint_flash_smem<4>(), stream, p);
+    else if (S <= 240) launch_k(joint_attn_flash_kernel<5>, dim3(grid), dim3(96), joint_flash_smem<5>(), stream, p);   // ViT: 197 tokens
+    else if (S <= 288) launch_k(joint_attn_flash_kernel<6>, dim3(grid), dim3(96), joint_flash_smem<6>(), stream, p);   // 196 image tokens + text
     else return MVLT_ERR_UNSUPPORTED;
   } else if (dtype == MVLT_F32) {
     const int npad = (S + 3) & ~3;
-    const int bytes = (3 * npad * 65 + npad + S * (npad + 1)) * 4;
-    if (bytes > 200 * 1024) return MVLT_ERR_UNSUPPORTED;
-    launch_k(attn_f32_kernel<64, false>, dim3(grid), dim3(256), bytes, stream, p, npad);
+    auto bytes_for = [&](int rb) { return (rb * 65 + 2 * npad * 65 + npad + rb * (npad + 1)) * 4; };
+    int rb = S;                                             // query rows per CTA: the whole sequence when it fits
+    while (rb > 8 && bytes_for(rb) > 200 * 1024) rb = (rb + 1) / 2;
+    if (bytes_for(rb) > 200 * 1024) return MVLT_ERR_UNSUPPORTED;
+    launch_k(attn_f32_kernel<64, false>, dim3(B, heads, (S + rb - 1) / rb), dim3(256), bytes_for(rb), stream, p, npad, rb);
   } else return MVLT_ERR_INVALID;
   MVLT_LAUNCH_CHECK();
   return MVLT_OK;

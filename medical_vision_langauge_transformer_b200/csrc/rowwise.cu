@@ -435,6 +435,24 @@ static int launch_ln(const void* in, long long ld_in, void* out, long long ld_ou
   return MVLT_OK;
 }
 
+// ViT token assembly (torchvision vision_transformer.py: `_process_input` + class token + `pos_embedding`, as used by
+// vfe.py:94-107): out[b, 0] = class_token + pos[0]; out[b, 1 + i] = patch_proj[b, i] + pos[1 + i].  One float4 per thread.
+__global__ void __launch_bounds__(256)
+vit_embed_kernel(const float* __restrict__ patches, const float* __restrict__ cls, const float* __restrict__ pos,
+                 float* __restrict__ out, int B, int n_patch, int D) {
+  pdl_grid_sync();
+  const int dq = D >> 2, S = n_patch + 1;
+  const long long total = (long long)B * S * dq;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dq) * 4;
+    const long long r = i / dq;
+    const int s = (int)(r % S), b = (int)(r / S);
+    const float4 a = s == 0 ? load4(cls + c) : load4(patches + ((long long)b * n_patch + s - 1) * D + c);
+    const float4 q = load4(pos + (long long)s * D + c);
+    store4(out + r * D + c, make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w));
+  }
+}
+
 }  // namespace mvlt
 
 using namespace mvlt;
@@ -521,6 +539,18 @@ extern "C" int mvlt_joint_embed(const void* feat, int feat_dtype, const int* img
   else if (out_dtype == MVLT_BF16)
     launch_k(joint_embed_kernel<6, bf16, bf16>, dim3(grid), dim3(256), 0, stream, (const bf16*)feat, img_index, ids, text_mask, image_mask, word_emb, typepos, (bf16*)out, (bf16*)out_bf16_copy, kmask, B, n_obj, L, D, cls_id, sep_id);
   else return MVLT_ERR_INVALID;
+  MVLT_LAUNCH_CHECK();
+  return MVLT_OK;
+}
+
+extern "C" int mvlt_vit_embed(const float* patches, const float* cls, const float* pos, float* out, int B, int n_patch, int D,
+                              cudaStream_t stream) {
+  if (!patches || !cls || !pos || !out || B <= 0 || n_patch <= 0 || D <= 0 || D % 4) return MVLT_ERR_INVALID;
+  if (((uintptr_t)patches & 15) || ((uintptr_t)cls & 15) || ((uintptr_t)pos & 15) || ((uintptr_t)out & 15)) return MVLT_ERR_INVALID;
+  const long long total = (long long)B * (n_patch + 1) * (D / 4);
+  long long g = (total + 255) / 256;
+  if (g > 148LL * 16) g = 148LL * 16;
+  launch_k(vit_embed_kernel, dim3((unsigned)g), dim3(256), 0, stream, patches, cls, pos, out, B, n_patch, D);
   MVLT_LAUNCH_CHECK();
   return MVLT_OK;
 }

@@ -19,8 +19,8 @@ from transformers import PreTrainedModel
 
 from .. import ops
 from .config import MVLBertConfig
-from .visual_feature_extractor import (SwinTransformer, act_dtype, default_precision, resnet50_without_poolfc,
-                                       resnet101_without_fc)
+from .visual_feature_extractor import (SwinTransformer, VisionTransformerBaseWithoutPooling, act_dtype, default_precision,
+                                       linear_patch_16x16, resnet50_without_poolfc, resnet101_without_fc)
 
 # Swin-S, the only backbone config the reference ships enabled (modules/swin_small_patch4_window7_224.yaml:1-8 on top
 # of the defaults in swin_transformer_config.py); `Conv_layer(config, swin_kwargs=...)` overrides it.
@@ -241,7 +241,8 @@ class Conv_layer(nn.Module):
     """model.py:186-266: Sequential(backbone, GELU) -> [B, 49, 768], returned in fp32 (as in the reference) in both
     precision modes.  Swin branch: the final LayerNorm and the GELU run as one kernel.  ResNet-101 / ResNet-50 branch
     (model.py:195-201): the GELU is the epilogue of the last bottleneck's GEMM, then `[B, 2048, 7, 7] -> [B, 49, 2048]`
-    (a no-op for NHWC activations) and `resnet_fc` (model.py:236, :263-264)."""
+    (a no-op for NHWC activations) and `resnet_fc` (model.py:236, :263-264).  `linear` (model.py:200-201) and `vit` /
+    `visiontransformer` (:227-228): 196 image tokens of width 768, GELU in the last kernel's epilogue."""
 
     def __init__(self, config, swin_kwargs=None, precision=None):
         super().__init__()
@@ -256,8 +257,10 @@ class Conv_layer(nn.Module):
             kw = dict(SWIN_SMALL)
             kw.update(swin_kwargs or {})
             backbone = SwinTransformer(precision=precision, **kw)
-        elif kind in ("linear", "vit", "visiontransformer"):
-            raise NotImplementedError(f"config.conv={config.conv!r}: only the Swin and ResNet backbones are on the accelerated path")
+        elif str(config.conv) == "linear":
+            backbone = linear_patch_16x16(precision=precision)
+        elif kind in ("vit", "visiontransformer"):
+            backbone = VisionTransformerBaseWithoutPooling(precision=precision)      # reference: ImageNet weights by URL
         else:
             raise NotImplementedError("no such config.conv")
         self.conv = nn.Sequential(backbone, nn.GELU())
@@ -281,6 +284,11 @@ class Conv_layer(nn.Module):
         backbone = self.conv[0]
         if isinstance(backbone, SwinTransformer):
             return backbone.forward_features(v, final_gelu=True, out_dtype=torch.float32)
+        if isinstance(backbone, VisionTransformerBaseWithoutPooling):
+            return backbone.forward_features(v, final_gelu=True)     # [B, 196, 768] (3-D: no reshape, width 768: no resnet_fc)
+        if isinstance(backbone, linear_patch_16x16):
+            a, H, W = backbone.forward_features(v, final_gelu=True)  # [B*196, 768] = the reshape/transpose of model.py:258-261
+            return a.view(v.shape[0], H * W, -1)
         a, H, W = backbone.forward_features(v, final_gelu=True)      # [B*49, 2048], GELU applied
         fw, fb = self._fc_packed(backbone.precision)
         feat = ops.linear(a, fw, fb, out_dtype=torch.float32)        # model.py:263-264 (channel == 2048)

@@ -13,6 +13,7 @@ The residual stream is fp32 in both precisions; GEMM operands are bf16 (tcgen05)
 """
 from __future__ import annotations
 
+import collections
 import os
 
 import torch
@@ -462,3 +463,154 @@ class resnet50_without_poolfc(ResNetWithoutFC):
 
     def __init__(self, pretrained=False, progress=False, precision=None):
         super().__init__([3, 4, 6, 3], pretrained, progress, precision)
+
+
+# ====================================================================================================================
+# Linear-patch and ViT backbones (vfe.py:47-107): 196 image tokens of width 768 (no resnet_fc), joint sequence 198 + L.
+# ====================================================================================================================
+class linear_patch_16x16(nn.Module):
+    """vfe.py:47-60: Conv2d(3, 768, k=16, s=16) + BatchNorm2d(768) + ReLU -> [B, 768, 14, 14].  Non-overlapping patches: the
+    convolution is a GEMM on the [B*196, 768] patch matrix (k = (c, ky, kx) = linear_patch.weight.view(768, -1) order) with the
+    eval-mode BatchNorm folded into weight and bias and the ReLU (+ the GELU of model.py:232-235) in the epilogue."""
+
+    def __init__(self, precision=None):
+        super().__init__()
+        self.linear_patch = nn.Conv2d(in_channels=3, out_channels=768, kernel_size=16, stride=16)
+        self.bn = nn.BatchNorm2d(768)
+        self.relu = nn.ReLU(inplace=True)
+        self.precision = precision or default_precision()
+        self._pk = None
+        self.taps = None
+
+    def packed(self):
+        ts = [self.linear_patch.weight, self.linear_patch.bias, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var]
+        key = (self.precision, ts[0].device, sum(t._version for t in ts), id(ts[0]))
+        if self._pk is None or self._pk[0] != key:
+            w, b = _fold_bn(self.linear_patch, self.bn)
+            self._pk = (key, w.reshape(w.shape[0], -1).to(act_dtype(self.precision)).contiguous(), b)
+        return self._pk[1], self._pk[2]
+
+    def forward_features(self, x, final_gelu: bool = False):
+        """-> NHWC matrix [B*196, 768] in the activation dtype."""
+        if self.training:
+            raise NotImplementedError("train-mode BatchNorm (batch statistics) is outside the accelerated forward path; call model.eval()")
+        if not x.is_cuda:
+            raise RuntimeError("mvlt_b200 backbones run on CUDA (sm_100a) only; move the model and inputs to the GPU")
+        w, b = self.packed()
+        B = x.shape[0]
+        a = ops.stem_im2col(x.contiguous().float(), 16, 16, 16, 0, w.shape[1], act_dtype(self.precision))
+        a = ops.linear(a, w, b, act=ops.ACT_RELU_GELU if final_gelu else ops.ACT_RELU)
+        H, W = x.shape[2] // 16, x.shape[3] // 16
+        if self.taps is not None and not final_gelu:
+            self.taps["linear_patch"] = a.float().view(B, H, W, -1).permute(0, 3, 1, 2).clone()
+        return a, H, W
+
+    def forward(self, x):
+        a, H, W = self.forward_features(x)
+        return a.float().view(x.shape[0], H, W, -1).permute(0, 3, 1, 2)
+
+
+class _ViTMLP(nn.Sequential):
+    """torchvision MLPBlock key layout: `0` Linear(768, 3072), `1` GELU, `2` Dropout, `3` Linear(3072, 768), `4` Dropout."""
+
+    def __init__(self, d, hidden):
+        super().__init__(nn.Linear(d, hidden), nn.GELU(), nn.Dropout(0.0), nn.Linear(hidden, d), nn.Dropout(0.0))
+
+
+class _ViTEncoderBlock(nn.Module):
+    def __init__(self, d, heads, hidden):
+        super().__init__()
+        self.num_heads = heads
+        self.ln_1 = nn.LayerNorm(d, eps=1e-6)
+        self.self_attention = nn.MultiheadAttention(d, heads, dropout=0.0, batch_first=True)   # in_proj_weight = Q|K|V packed
+        self.dropout = nn.Dropout(0.0)
+        self.ln_2 = nn.LayerNorm(d, eps=1e-6)
+        self.mlp = _ViTMLP(d, hidden)
+
+
+class _ViTEncoder(nn.Module):
+    def __init__(self, seq, layers, heads, d, hidden):
+        super().__init__()
+        self.pos_embedding = nn.Parameter(torch.empty(1, seq, d).normal_(std=0.02))
+        self.dropout = nn.Dropout(0.0)
+        self.layers = nn.Sequential(collections.OrderedDict(
+            (f"encoder_layer_{i}", _ViTEncoderBlock(d, heads, hidden)) for i in range(layers)))
+        self.ln = nn.LayerNorm(d, eps=1e-6)
+
+
+class VisionTransformerBaseWithoutPooling(nn.Module):
+    """vfe.py:66-107: torchvision ViT-B/16 (`vit_b_16` key layout: class_token, conv_proj, encoder.pos_embedding,
+    encoder.layers.encoder_layer_{i}.{ln_1, self_attention.{in_proj_weight, in_proj_bias, out_proj}, ln_2, mlp.{0,3}}, encoder.ln,
+    heads.head) whose forward returns the 196 patch tokens `x[:, 1:]` without the classifier.  Pre-LN blocks on the same
+    kernels as the BERT encoder: LayerNorm -> packed-QKV GEMM -> joint attention (197 tokens, no mask) -> out_proj GEMM
+    accumulating in place into the fp32 stream -> LayerNorm -> fc1 + GELU -> fc2 in place; final LayerNorm."""
+
+    def __init__(self, pretrained=False, progress=False, precision=None, **kwargs):
+        super().__init__()
+        if pretrained:
+            raise RuntimeError("no network: torchvision ImageNet weights cannot be downloaded here; load a state_dict "
+                               "(the key layout is torchvision's vit_b_16) after construction")
+        d, heads, hidden, layers, patch, img = 768, 12, 3072, 12, 16, 224
+        self.image_size, self.patch_size, self.hidden_dim, self.num_heads = img, patch, d, heads
+        self.precision = precision or default_precision()
+        self.class_token = nn.Parameter(torch.zeros(1, 1, d))
+        self.conv_proj = nn.Conv2d(3, d, kernel_size=patch, stride=patch)
+        self.seq_length = (img // patch) ** 2 + 1
+        self.encoder = _ViTEncoder(self.seq_length, layers, heads, d, hidden)
+        self.heads = nn.Sequential(collections.OrderedDict(head=nn.Linear(d, 1000)))      # constructed, never applied (vfe.py:101-105)
+        fan_in = 3 * patch * patch
+        nn.init.trunc_normal_(self.conv_proj.weight, std=(1 / fan_in) ** 0.5)
+        nn.init.zeros_(self.conv_proj.bias)
+        self._pk = None
+        self.taps = None
+
+    def packed(self):
+        ps = list(self.parameters())
+        key = (self.precision, ps[0].device, sum(p._version for p in ps), id(ps[0]))
+        if self._pk is None or self._pk[0] != key:
+            wd = act_dtype(self.precision)
+            f32 = lambda t: t.detach().float().contiguous()
+            wcast = lambda t: t.detach().to(wd).contiguous()
+            pk = dict(proj_w=wcast(self.conv_proj.weight.reshape(self.hidden_dim, -1)), proj_b=f32(self.conv_proj.bias),
+                      cls=f32(self.class_token.reshape(-1)), pos=f32(self.encoder.pos_embedding.reshape(self.seq_length, -1)),
+                      ln_w=f32(self.encoder.ln.weight), ln_b=f32(self.encoder.ln.bias), layers=[])
+            for blk in self.encoder.layers:
+                at = blk.self_attention
+                pk["layers"].append(dict(
+                    n1w=f32(blk.ln_1.weight), n1b=f32(blk.ln_1.bias), n2w=f32(blk.ln_2.weight), n2b=f32(blk.ln_2.bias),
+                    qkv_w=wcast(at.in_proj_weight), qkv_b=f32(at.in_proj_bias),
+                    out_w=wcast(at.out_proj.weight), out_b=f32(at.out_proj.bias),
+                    fc1_w=wcast(blk.mlp[0].weight), fc1_b=f32(blk.mlp[0].bias),
+                    fc2_w=wcast(blk.mlp[3].weight), fc2_b=f32(blk.mlp[3].bias)))
+            self._pk = (key, pk)
+        return self._pk[1]
+
+    def forward_features(self, x, final_gelu: bool = False):
+        """-> fp32 [B, 196, 768]: the encoder output without the class token (+ the nn.GELU of model.py:232-235)."""
+        if not x.is_cuda:
+            raise RuntimeError("mvlt_b200 backbones run on CUDA (sm_100a) only; move the model and inputs to the GPU")
+        B, _, H, W = x.shape
+        assert H == self.image_size and W == self.image_size, f"Wrong image height/width! Expected {self.image_size} but got {H}x{W}!"
+        pk = self.packed()
+        adt = act_dtype(self.precision)
+        p = self.patch_size
+        a = ops.stem_im2col(x.contiguous().float(), p, p, p, 0, 3 * p * p, adt)
+        patches = ops.linear(a, pk["proj_w"], pk["proj_b"], out_dtype=torch.float32)
+        X = ops.vit_embed(patches, pk["cls"], pk["pos"], B)                       # fp32 [B*197, 768]
+        S = self.seq_length
+        kmask = torch.zeros((B, S), device=x.device, dtype=torch.float32)
+        for li, (blk, w) in enumerate(zip(self.encoder.layers, pk["layers"])):
+            h = ops.layernorm(X, w["n1w"], w["n1b"], blk.ln_1.eps, adt)
+            qkv = ops.linear(h, w["qkv_w"], w["qkv_b"])
+            ctx = ops.joint_attention(qkv, kmask, B, S, self.num_heads, False, S)
+            ops.linear(ctx, w["out_w"], w["out_b"], residual=X, out=X)
+            h = ops.layernorm(X, w["n2w"], w["n2b"], blk.ln_2.eps, adt)
+            f = ops.linear(h, w["fc1_w"], w["fc1_b"], act=ops.ACT_GELU)
+            ops.linear(f, w["fc2_w"], w["fc2_b"], residual=X, out=X)
+            if self.taps is not None and li in (0, len(pk["layers"]) - 1):
+                self.taps[f"vit{li}"] = X.clone().view(B, S, -1)
+        out = ops.layernorm(X, pk["ln_w"], pk["ln_b"], self.encoder.ln.eps, torch.float32, gelu=final_gelu)
+        return out.view(B, S, -1)[:, 1:]
+
+    def forward(self, x):
+        return self.forward_features(x)

@@ -302,6 +302,19 @@ def joint_embed(feat: torch.Tensor, ids: torch.Tensor, text_mask: Optional[torch
     return out, copy, kmask
 
 
+def vit_embed(patches: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, B: int) -> torch.Tensor:
+    """[B*n_patch, D] projected patches + class token + position embedding -> fp32 [B*(1+n_patch), D]."""
+    lib = _lib.ensure_init()
+    n_patch, D = patches.shape[0] // B, patches.shape[1]
+    for t in (patches, cls, pos):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+    assert cls.numel() == D and pos.numel() == (n_patch + 1) * D
+    out = torch.empty((B * (n_patch + 1), D), device=patches.device, dtype=torch.float32)
+    rc = lib.mvlt_vit_embed(patches.data_ptr(), cls.data_ptr(), pos.data_ptr(), out.data_ptr(), B, n_patch, D, _stream())
+    _lib.check(rc, "mvlt_vit_embed")
+    return out
+
+
 def joint_attention(qkv: torch.Tensor, kmask: torch.Tensor, B: int, S: int, heads: int, seq2seq: bool, obj_end: int,
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.ensure_init()

@@ -24,7 +24,8 @@ import torch
 
 _BUFFERS = ("relative_position_index", "attn_mask", "position_ids", "num_batches_tracked")
 _RESNET = re.compile(r"^conv\.conv\.0\.(conv1|bn1|layer[1-4]|fc)\.")      # torchvision ResNet keys under Conv_layer
-_BATCHNORM = re.compile(r"\.(bn\d|downsample\.1)\.(weight|bias|running_mean|running_var)$")
+_BATCHNORM = re.compile(r"\.(bn\d?|downsample\.1)\.(weight|bias|running_mean|running_var)$")
+_VIT_LINEAR = re.compile(r"^conv\.conv\.0\.(class_token$|conv_proj\.|encoder\.|heads\.|linear_patch\.|bn\.)")   # vfe.py:47-107
 
 
 def _gen(name: str, seed: int) -> torch.Generator:
@@ -40,6 +41,8 @@ def synth_tensor(name: str, shape, seed: int = 0, flavour: str = "stress") -> to
     leaf = name.rsplit(".", 1)[-1]
     if _RESNET.match(name) and ".fc." not in name:
         return _synth_resnet(name, shape, g, flavour)
+    if _VIT_LINEAR.match(name):
+        return _synth_vit_linear(name, shape, g, flavour)
     is_swin = name.startswith("conv.conv.0.")
     is_ln = any(t in name for t in ("norm", "LayerNorm")) and "downsample.reduction" not in name
     if is_ln:
@@ -86,6 +89,36 @@ def _synth_resnet(name: str, shape, g: torch.Generator, flavour: str) -> torch.T
     assert leaf == "weight" and len(shape) == 4, name
     n, c, r, s = shape
     return randn(math.sqrt(2.0 / (n * r * s))) if flavour == "init" else randn(math.sqrt(2.0 / (c * r * s)))
+
+
+def _synth_vit_linear(name: str, shape, g: torch.Generator, flavour: str) -> torch.Tensor:
+    """torchvision ViT-B/16 trunk (vfe.py:66-107) and the linear-patch stem (vfe.py:47-60).  "init": unit LayerNorm / BatchNorm,
+    zero biases, small normal weights; "stress": non-trivial norms and biases, O(1) attention logits, damped residual
+    branches (out_proj / mlp.3) so twelve pre-LN blocks stay O(1)."""
+    leaf = name.rsplit(".", 1)[-1]
+    randn = lambda s=1.0: torch.randn(shape, generator=g) * s
+    init = flavour == "init"
+    if _BATCHNORM.search(name):
+        if init:
+            return torch.ones(shape) if leaf in ("weight", "running_var") else torch.zeros(shape)
+        if leaf == "weight":
+            return 1.0 + randn(0.1)
+        return 0.8 + 0.4 * torch.rand(shape, generator=g) if leaf == "running_var" else randn(0.05)
+    if ".ln_1." in name or ".ln_2." in name or ".encoder.ln." in name:
+        if init:
+            return torch.ones(shape) if leaf == "weight" else torch.zeros(shape)
+        return 1.0 + randn(0.1) if leaf == "weight" else randn(0.05)
+    if leaf == "class_token":
+        return torch.zeros(shape) if init else randn(0.5)
+    if leaf == "pos_embedding":
+        return randn(0.02) if init else randn(0.2)
+    if leaf in ("bias", "in_proj_bias"):
+        return torch.zeros(shape) if init else randn(0.02)
+    fan_in = int(math.prod(shape[1:]))
+    if leaf == "in_proj_weight":
+        return randn(0.03) if init else randn(1.5 / math.sqrt(fan_in))
+    damp = 0.5 if (".out_proj." in name or ".mlp.3." in name) and not init else 1.0
+    return randn(damp / math.sqrt(fan_in))
 
 
 def synth_state_dict(shapes: Mapping[str, torch.Size], seed: int = 0, flavour: str = "stress") -> Dict[str, torch.Tensor]:

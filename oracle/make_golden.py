@@ -38,7 +38,12 @@ def attach_taps(model, taps: dict):
     """Forward hooks on the reference modules; names match oracle.mvlt_oracle taps."""
     hs = []
     swin = model.conv.conv[0]
-    if hasattr(swin, "layer1"):           # ResNet trunk (vfe.py:7-44): stem output after the max-pool, then each stage
+    if hasattr(swin, "linear_patch"):     # linear-patch stem (vfe.py:47-60): its [B,768,14,14] output
+        hs.append(swin.register_forward_hook(lambda m, i, o: taps.__setitem__("linear_patch", o)))
+    elif hasattr(swin, "class_token"):    # ViT trunk (vfe.py:66-107): residual stream after the first and the last block
+        for li in (0, 11):
+            hs.append(swin.encoder.layers[li].register_forward_hook(lambda m, i, o, k=f"vit{li}": taps.__setitem__(k, o)))
+    elif hasattr(swin, "layer1"):           # ResNet trunk (vfe.py:7-44): stem output after the max-pool, then each stage
         hs.append(swin.maxpool.register_forward_hook(lambda m, i, o: taps.__setitem__("stem", o)))
         for li in (1, 2, 3, 4):
             hs.append(getattr(swin, f"layer{li}").register_forward_hook(
@@ -133,7 +138,7 @@ def write_state_dict_keys():
     out = {}
     for task in ("vqa", "retrieval", "pretrain"):
         out[task] = {k: list(v.shape) for k, v in build_reference_model(task).state_dict().items()}
-    for conv in ("resnet101", "resnet50"):
+    for conv in ("resnet101", "resnet50", "linear", "vit"):
         m = build_reference_model("retrieval", max_length=80, conv=conv)
         out[f"retrieval_{conv}"] = {k: list(v.shape) for k, v in m.state_dict().items()}
     with open(os.path.join(GOLDEN_DIR, "state_dict_keys.json"), "w") as f:
@@ -153,6 +158,8 @@ def main():
         "rank6": case_rank,
         "retrieval_resnet101": lambda: case_retrieval("stress", 1.0, conv="resnet101"),   # BASELINE.json configs[4] backbone
         "retrieval_resnet50": lambda: case_retrieval("stress", 1.0, conv="resnet50"),
+        "retrieval_linear": lambda: case_retrieval("stress", 1.0, conv="linear"),
+        "retrieval_vit": lambda: case_retrieval("stress", 1.0, conv="vit"),
     }
     only = sys.argv[1:]                         # `python -m oracle.make_golden NAME...` regenerates just those cases
     for name, fn in cases.items():

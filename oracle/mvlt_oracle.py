@@ -183,12 +183,62 @@ def resnet_forward(sd: SD, img: Tensor, prefix: str = "conv.conv.0.", layers=RES
     return x
 
 
+# ----------------------------------------------------------------------------------------------
+# Linear-patch stem (vfe.py:47-60) and ViT-B/16 trunk (vfe.py:66-107; third-party arithmetic: torchvision
+# models/vision_transformer.py + torch.nn.MultiheadAttention, reference pin torchvision>=0.12.0)
+# ----------------------------------------------------------------------------------------------
+def linear_patch_forward(sd: SD, img: Tensor, prefix: str = "conv.conv.0.") -> Tensor:
+    """vfe.py:55-60: Conv2d(3,768,k=16,s=16) -> BatchNorm2d (eval) -> ReLU -> [B,768,14,14]."""
+    x = F.conv2d(img, sd[prefix + "linear_patch.weight"], sd[prefix + "linear_patch.bias"], stride=16)
+    return F.relu(_bn_eval(sd, prefix + "bn.", x))
+
+
+def vit_forward(sd: SD, img: Tensor, prefix: str = "conv.conv.0.", heads: int = 12, taps: Optional[dict] = None) -> Tensor:
+    """vfe.py:89-107 over torchvision's VisionTransformer: `_process_input` (conv_proj 16x16/16 -> [B,196,768]), class token,
+    + pos_embedding, 12 pre-LN EncoderBlocks (ln_1 -> MultiheadAttention with packed in_proj -> + x; ln_2 -> Linear, GELU,
+    Linear -> + x), final LayerNorm (eps 1e-6), and the reference drops the class token: x[:, 1:] -> [B,196,768]."""
+    x = F.conv2d(img, sd[prefix + "conv_proj.weight"], sd[prefix + "conv_proj.bias"], stride=16).flatten(2).transpose(1, 2)
+    B, _, D = x.shape
+    x = torch.cat([sd[prefix + "class_token"].expand(B, -1, -1), x], 1) + sd[prefix + "encoder.pos_embedding"]
+    n_layers = sum(1 for k in sd if k.startswith(prefix + "encoder.layers.") and k.endswith(".ln_1.weight"))
+    hd = D // heads
+    for i in range(n_layers):
+        p = f"{prefix}encoder.layers.encoder_layer_{i}."
+        h = F.layer_norm(x, (D,), sd[p + "ln_1.weight"], sd[p + "ln_1.bias"], 1e-6)
+        qkv = F.linear(h, sd[p + "self_attention.in_proj_weight"], sd[p + "self_attention.in_proj_bias"])
+        q, k, v = (t.view(B, -1, heads, hd).transpose(1, 2) for t in qkv.chunk(3, -1))
+        a = ((q @ k.transpose(-1, -2)) / math.sqrt(hd)).softmax(-1) @ v
+        a = a.transpose(1, 2).reshape(B, -1, D)
+        x = x + F.linear(a, sd[p + "self_attention.out_proj.weight"], sd[p + "self_attention.out_proj.bias"])
+        h = F.layer_norm(x, (D,), sd[p + "ln_2.weight"], sd[p + "ln_2.bias"], 1e-6)
+        x = x + F.linear(F.gelu(F.linear(h, sd[p + "mlp.0.weight"], sd[p + "mlp.0.bias"])), sd[p + "mlp.3.weight"], sd[p + "mlp.3.bias"])
+        if taps is not None and i in (0, n_layers - 1):
+            taps[f"vit{i}"] = x
+    x = F.layer_norm(x, (D,), sd[prefix + "encoder.ln.weight"], sd[prefix + "encoder.ln.bias"], 1e-6)
+    return x[:, 1:]
+
+
 def conv_layer(sd: SD, img: Tensor, taps: Optional[dict] = None) -> Tensor:
+    feat = _conv_layer(sd, img, taps)
+    if taps is not None:
+        taps["image_feature"] = feat
+    return feat
+
+
+def _conv_layer(sd: SD, img: Tensor, taps: Optional[dict] = None) -> Tensor:
     """model.py:232-235,255-266 — Sequential(backbone, GELU); 4-D branch.  Swin: feature dim 768 so no resnet_fc.
     ResNet (keys `conv.conv.0.layer1...`): [B,2048,7,7] -> reshape/transpose [B,49,2048] (:258-261) -> resnet_fc (:263-264);
     the depth is read off the state_dict (layer3 has 23 blocks for resnet101, 6 for resnet50)."""
     if img.dim() == 5:                       # IU-Xray two-view input, model.py:240-253: objects of both views concatenated
-        return torch.cat((conv_layer(sd, img[:, 0], taps), conv_layer(sd, img[:, 1])), dim=1)
+        return torch.cat((_conv_layer(sd, img[:, 0], taps), _conv_layer(sd, img[:, 1])), dim=1)
+    if "conv.conv.0.linear_patch.weight" in sd:   # model.py:200-201, :258-261: [B,768,14,14] -> [B,196,768]; width 768: no resnet_fc
+        x = linear_patch_forward(sd, img)
+        if taps is not None:
+            taps["linear_patch"] = x
+        x = F.gelu(x)
+        return x.reshape(x.shape[0], x.shape[1], -1).transpose(1, 2)
+    if "conv.conv.0.class_token" in sd:           # model.py:227-228: 3-D output, no reshape
+        return F.gelu(vit_forward(sd, img, taps=taps))
     if "conv.conv.0.layer1.0.conv1.weight" in sd:
         layers = tuple(sum(1 for k in sd if k.startswith(f"conv.conv.0.layer{i}.") and k.endswith(".conv1.weight"))
                        for i in (1, 2, 3, 4))

@@ -192,6 +192,8 @@ def _install_resnet_shim(ref_vfe):
         name = url.rsplit("/", 1)[-1]
         return getattr(torchvision.models, name)(weights=None).state_dict()
 
+    if not hasattr(torchvision.models.vision_transformer, "model_urls"):       # vfe.py:84-87 (ViT variant)
+        torchvision.models.vision_transformer.model_urls = {"vit_b_16": "offline://vit_b_16"}
     ref_vfe.load_state_dict_from_url = _offline_state_dict
 
 
@@ -217,7 +219,7 @@ def build_reference_model(task: str, seed: int = 0, **cfg_kw):
     import torch
     ref_model, _, ref_vfe = import_reference()
     cfg = make_reference_config(task, **cfg_kw)
-    if cfg.conv.startswith("resnet"):
+    if cfg.conv.startswith("resnet") or cfg.conv.lower() in ("vit", "visiontransformer"):
         _install_resnet_shim(ref_vfe)
     cls = {"vqa": ref_model.MVLBertForVQA, "retrieval": ref_model.MVLBertForRetrieval,
            "pretrain": ref_model.MVLBertForPretraining}[task]

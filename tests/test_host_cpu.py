@@ -46,7 +46,7 @@ def test_state_dict_layout_matches_reference(task):
     assert all(list(sd[k].shape) == ref[k] for k in ref)
 
 
-@pytest.mark.parametrize("conv", ["resnet101", "resnet50"])
+@pytest.mark.parametrize("conv", ["resnet101", "resnet50", "linear", "vit"])
 def test_resnet_state_dict_layout_matches_reference(conv):
     """torchvision ResNet key layout under `conv.conv.0.` (incl. the never-applied fc and the BatchNorm buffers) + resnet_fc."""
     from medical_vision_langauge_transformer_b200.modules import config as C, model as M

@@ -46,6 +46,22 @@ def test_oracle_retrieval_matches_reference_golden(case):
     _check_taps(taps, g["taps"])
 
 
+@pytest.mark.parametrize("conv", ["linear", "vit"])
+def test_oracle_linear_and_vit_retrieval_match_reference_golden(conv):
+    """Linear-patch stem (vfe.py:47-60) and ViT-B/16 trunk (vfe.py:66-107 over torchvision's VisionTransformer): 196 image
+    tokens, joint sequence 278 at L = 80."""
+    g = torch.load(os.path.join(GOLDEN, f"retrieval_{conv}.pt"))
+    sd = _sd(f"retrieval_{conv}", g["weight_seed"], g["flavour"])
+    x, ids = synth.synth_images(g["B"], g["data_seed"], g["img_scale"]), synth.synth_token_ids(g["B"], g["L"], g["data_seed"])
+    taps = {}
+    with torch.no_grad():
+        prob = O.retrieval_forward(sd, x, ids, taps=taps)
+        logits = O.retrieval_forward(sd, x, ids, return_logits=True)
+    assert torch.allclose(prob, g["prob"], atol=1e-6) and torch.allclose(logits, g["logits"], atol=1e-5)
+    assert taps["image_feature"].shape == (g["B"], 196, 768)
+    _check_taps(taps, g["taps"])
+
+
 @pytest.mark.parametrize("conv", ["resnet101", "resnet50"])
 def test_oracle_resnet_retrieval_matches_reference_golden(conv):
     """ResNet backbones (vfe.py:7-44 over torchvision's Bottleneck ResNet) + resnet_fc + the joint encoder."""

@@ -193,6 +193,31 @@ def test_resnet_retrieval_vs_reference_golden(cuda, conv, precision):
     assert prob.dtype == torch.float32 and prob.shape == (g["B"], 2)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("conv", ["linear", "vit"])
+def test_linear_and_vit_retrieval_vs_reference_golden(cuda, conv, precision):
+    """config.conv = 'linear' (vfe.py:47-60) and 'vit' (vfe.py:66-107): 196 image tokens, S = 278 through the 288-key joint
+    attention; the ViT encoder blocks run on the BERT kernels (197-token attention, no mask)."""
+    from medical_vision_langauge_transformer_b200 import synth
+    g = torch.load(os.path.join(GOLDEN, f"retrieval_{conv}.pt"))
+    model, _ = build(conv, precision, g["L"])
+    x = synth.synth_images(g["B"], g["data_seed"], g["img_scale"]).cuda()
+    ids = synth.synth_token_ids(g["B"], g["L"], g["data_seed"]).cuda()
+    taps = {}
+    model.conv.conv[0].taps = model.MVLBert.taps = taps
+    with torch.no_grad():
+        prob = model(x, ids)
+        logits = model(x, ids, image_text_label=torch.zeros(g["B"], dtype=torch.long, device="cuda"))
+    assert taps["image_feature"].shape == (g["B"], 196, 768)
+    worst = probe_check(taps, g["taps"], 1e-4 if precision == "fp32" else 3e-2, f"{conv}/{precision}")
+    print(conv, precision, {k: f"{v:.1e}" for k, v in worst.items()}, "logits", relerr(logits, g["logits"]))
+    if precision == "fp32":
+        assert relerr(logits, g["logits"]) < 1e-4 and relerr(prob, g["prob"]) < 1e-4
+    else:
+        assert torch.allclose(logits.cpu(), g["logits"], rtol=1e-2, atol=1e-2), (logits, g["logits"])
+        assert relerr(prob, g["prob"]) < 1e-2
+
+
 def test_resnet_backbone_module_surface(cuda):
     """`resnet101_without_fc()(x)` keeps the reference's output contract (vfe.py:14-24): NCHW [B, 2048, 7, 7]; checked
     against the oracle trunk on another seed, and train mode is rejected (no batch-statistics kernel)."""
