@@ -65,7 +65,7 @@ class MVLBertRetrieval(MVLBertConfig):
 
 
 class MVLBertConfigForImageCaption(MVLBertConfig):
-    """reference config.py:64-72 (kept for config compatibility; the generation path itself is out of scope)."""
+    """reference config.py:64-72 (report generation; the teacher-forced pass runs natively, the decode loop does not)."""
     _task_defaults = dict(lr=1e-5, max_length=80, is_decoder=True, attention_probs_dropout_prob=0.1,
                           hidden_dropout_prob=0.1)
 
@@ -76,7 +76,8 @@ class MVLBertConfigForImageCaption(MVLBertConfig):
 def offline_config(task: str, conv: str = "swintransformer", max_length: int = 80, **overrides) -> MVLBertConfig:
     """What `Config.from_pretrained('bert-base-uncased')` + `update_special_tokens(tokenizer)` yields, without network:
     bert-base defaults, vocab 30522, [CLS]=101 [SEP]=102 [MASK]=103 [END]=104 (dataset/bert-base-uncased/vocab.txt)."""
-    cls = {"vqa": MVLBertConfigforVQA, "retrieval": MVLBertRetrieval, "pretrain": MVLBertPretrainConfig}[task]
+    cls = {"vqa": MVLBertConfigforVQA, "retrieval": MVLBertRetrieval, "pretrain": MVLBertPretrainConfig,
+           "caption": MVLBertConfigForImageCaption}[task]
     cfg = cls()
     cfg.conv = conv
     cfg.vocab_size = 30522

@@ -7,7 +7,7 @@ directories and whole-model pickles — load unchanged.  Weights keep PyTorch-de
 the reference, where `init_weights()` is never called (model.py:365).
 
 Out of scope here: the KV-cache decode branch of `get_embedding` (model.py:82-108) and
-`MVLBertForImageCaption`; the ViT/linear backbones of `Conv_layer` (model.py:200-201,227-228).
+the greedy / beam-search decode of `MVLBertForImageCaption` (its teacher-forced pass is here).
 """
 from __future__ import annotations
 
@@ -443,3 +443,50 @@ class MVLBertForPretraining(_PackedMixin, MVLBertPretrainedModel):
         itm_logits = ops.linear_small(self.MVLBert.pool(hidden, shadow, B, S), pk["itm_w"], pk["itm_b"])
         acc = ops.masked_ce(itm_logits, image_text_label.reshape(-1), 2, -100)
         return mlm_loss.mean() + acc[0] / acc[1]
+
+
+class MVLBertForImageCaption(_PackedMixin, MVLBertPretrainedModel):
+    """model.py:479-550: report generation / image captioning.  `forward(image, caption, num_beams=0, learning_strategy)` is the
+    teacher-forced pass (`encode_forward`, model.py:518-550: seq2seq mask, MLM head over the text positions ('unilm') or over
+    [SEP], t1..t(n-1) ('normal')) -> logits [B, vocab, L] as in the reference.  Greedy / beam search (num_beams >= 1) decode
+    through the KV-cache branch of `get_embedding` (model.py:82-108), which is outside the accelerated path."""
+
+    def __init__(self, config, tokenizer=None):
+        super().__init__(config)
+        self.config = config
+        assert config.is_decoder, 'config.is_decoder should be True if you want to run image caption for testing'
+        self.MVLBert = MVLBert(config, add_pooling_layer=True)
+        self.conv = Conv_layer(config)
+        self.tokenizer = tokenizer
+        self.MLM_head_seq2seq = _OnlyMLMHead(config)
+
+    def _pack_params(self):
+        return self.MLM_head_seq2seq.parameters()
+
+    def _pack(self):
+        p, wd = self.MLM_head_seq2seq.predictions, act_dtype(self.precision)
+        f32 = lambda x: x.detach().float().contiguous()
+        return dict(tw=p.transform.dense.weight.detach().to(wd).contiguous(), tb=f32(p.transform.dense.bias),
+                    lw=f32(p.transform.LayerNorm.weight), lb=f32(p.transform.LayerNorm.bias),
+                    dw=p.decoder.weight.detach().to(wd).contiguous(), db=f32(p.decoder.bias))
+
+    def forward(self, image, caption, num_beams=0, learning_strategy="unilm", sample_mode="greedy"):
+        if num_beams >= 1:
+            raise NotImplementedError("greedy / beam search decode (model.py:636-984, KV-cache branch of get_embedding) is "
+                                      "outside the accelerated forward path; num_beams=0 runs the teacher-forced pass")
+        if learning_strategy not in ("unilm", "normal"):
+            raise NotImplementedError("learning_strategy:", learning_strategy, "is not implemented! Try 'unilm' or 'normal'.")
+        feat, hidden, shadow, B, S = self._trunk(image, caption, None, True)
+        n_obj, L, D = feat.shape[1], caption.shape[1], hidden.shape[1]
+        # 'unilm': hidden states of t1..tn ; 'normal': [SEP], t1..t(n-1) = the same window shifted one row up (model.py:536-544)
+        first = n_obj + 2 if learning_strategy == "unilm" else n_obj + 1
+        src = shadow if shadow is not None else hidden
+        rows = src.view(B, S, D)[:, first:first + L].reshape(B * L, D)
+        w = self.packed()
+        t = ops.linear(rows, w["tw"], w["tb"], act=ops.ACT_GELU, out_dtype=torch.float32)
+        t = ops.layernorm(t, w["lw"], w["lb"], self.config.layer_norm_eps, act_dtype(self.precision))
+        V = w["dw"].shape[0]
+        ld = (V + 31) // 32 * 32
+        logits = torch.empty((B * L, ld), device=t.device, dtype=torch.float32)[:, :V]
+        ops.linear(t, w["dw"], w["db"], out=logits)
+        return logits.view(B, L, V).transpose(1, 2)          # batch, vocab_size, seq_len (model.py:534)

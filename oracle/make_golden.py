@@ -115,6 +115,19 @@ def case_pretrain(B=2, L=80):
     return out
 
 
+def case_caption(B=2, L=40):
+    """MVLBertForImageCaption teacher-forced pass (num_beams=0, model.py:518-550), both learning strategies; logits are
+    [B, 30522, L] — stored as probes."""
+    m = build_reference_model("caption", max_length=L)
+    synth.load_synth(m, 0, "stress")
+    x, ids = synth.synth_images(B, 5, 1.0), synth.synth_token_ids(B, L, 5)
+    out = {"task": "caption", "flavour": "stress", "img_scale": 1.0, "B": B, "L": L, "weight_seed": 0, "data_seed": 5}
+    with torch.no_grad():
+        for strategy in ("unilm", "normal"):
+            out[strategy] = probe(m(x, ids, 0, strategy), "caption_" + strategy)
+    return out
+
+
 def case_rank(N=6, L=80):
     """run_retrieval.py test split: row-major N*N pair enumeration through the reference model."""
     import numpy as np
@@ -136,7 +149,7 @@ def write_state_dict_keys():
     """tests/golden/state_dict_keys.json: key -> shape of the REAL reference's task models, in state_dict order."""
     import json
     out = {}
-    for task in ("vqa", "retrieval", "pretrain"):
+    for task in ("vqa", "retrieval", "pretrain", "caption"):
         out[task] = {k: list(v.shape) for k, v in build_reference_model(task).state_dict().items()}
     for conv in ("resnet101", "resnet50", "linear", "vit"):
         m = build_reference_model("retrieval", max_length=80, conv=conv)
@@ -158,6 +171,7 @@ def main():
         "rank6": case_rank,
         "retrieval_resnet101": lambda: case_retrieval("stress", 1.0, conv="resnet101"),   # BASELINE.json configs[4] backbone
         "retrieval_resnet50": lambda: case_retrieval("stress", 1.0, conv="resnet50"),
+        "caption_stress": case_caption,
         "retrieval_linear": lambda: case_retrieval("stress", 1.0, conv="linear"),
         "retrieval_vit": lambda: case_retrieval("stress", 1.0, conv="vit"),
     }

@@ -374,6 +374,18 @@ def pretrain_forward(sd: SD, image: Tensor, caption_masked: Tensor, caption_labe
     return mlm.mean() + itm.mean()
 
 
+def caption_encode_forward(sd: SD, image: Tensor, caption: Tensor, learning_strategy: str = "unilm") -> Tensor:
+    """model.py:518-550 (`MVLBertForImageCaption.encode_forward`, reached with num_beams=0): seq2seq mask, MLM head (HF:488-512)
+    over t1..tn ('unilm') or [SEP], t1..t(n-1) ('normal') -> logits [B, vocab, L]."""
+    feat = conv_layer(sd, image)
+    h, _ = mvlbert(sd, caption, feat, seq2seq=True)
+    n_obj, L = feat.shape[1], caption.shape[1]
+    first = n_obj + 2 if learning_strategy == "unilm" else n_obj + 1
+    p = "MLM_head_seq2seq.predictions."
+    t = head_transform(sd, p + "transform.", h[:, first:first + L])
+    return F.linear(t, sd[p + "decoder.weight"], sd[p + "decoder.bias"]).transpose(1, 2)
+
+
 # ----------------------------------------------------------------------------------------------
 # N x N retrieval scoring and ranking
 # ----------------------------------------------------------------------------------------------

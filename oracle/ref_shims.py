@@ -202,7 +202,7 @@ def make_reference_config(task: str, max_length: int = 80, result_num: int = 224
     """Config objects as the run_*.py scripts would build them, without network."""
     _, ref_config, _ = import_reference()
     cls = {"vqa": ref_config.MVLBertConfigforVQA, "retrieval": ref_config.MVLBertRetrieval,
-           "pretrain": ref_config.MVLBertPretrainConfig}[task]
+           "pretrain": ref_config.MVLBertPretrainConfig, "caption": ref_config.MVLBertConfigForImageCaption}[task]
     cfg = cls()
     cfg.conv = conv
     cfg.vocab_size = 30522
@@ -222,7 +222,7 @@ def build_reference_model(task: str, seed: int = 0, **cfg_kw):
     if cfg.conv.startswith("resnet") or cfg.conv.lower() in ("vit", "visiontransformer"):
         _install_resnet_shim(ref_vfe)
     cls = {"vqa": ref_model.MVLBertForVQA, "retrieval": ref_model.MVLBertForRetrieval,
-           "pretrain": ref_model.MVLBertForPretraining}[task]
+           "pretrain": ref_model.MVLBertForPretraining, "caption": ref_model.MVLBertForImageCaption}[task]
     with _reference_cwd():
         torch.manual_seed(seed)
         model = cls(cfg)

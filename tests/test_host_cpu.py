@@ -36,11 +36,12 @@ def test_ops_fail_loudly_without_a_gpu():
         ops.softmax_rows(torch.zeros(2, 2))
 
 
-@pytest.mark.parametrize("task", ["vqa", "retrieval", "pretrain"])
+@pytest.mark.parametrize("task", ["vqa", "retrieval", "pretrain", "caption"])
 def test_state_dict_layout_matches_reference(task):
     from medical_vision_langauge_transformer_b200.modules import config as C, model as M
     ref = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))[task]
-    cls = {"vqa": M.MVLBertForVQA, "retrieval": M.MVLBertForRetrieval, "pretrain": M.MVLBertForPretraining}[task]
+    cls = {"vqa": M.MVLBertForVQA, "retrieval": M.MVLBertForRetrieval, "pretrain": M.MVLBertForPretraining,
+           "caption": M.MVLBertForImageCaption}[task]
     sd = cls(C.offline_config(task)).state_dict()
     assert list(sd) == list(ref)                         # same keys, same order
     assert all(list(sd[k].shape) == ref[k] for k in ref)

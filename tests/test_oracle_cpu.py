@@ -103,6 +103,18 @@ def test_oracle_pretrain_matches_reference_golden():
         assert abs(loss.item() - g[branch]["loss"].item()) < 1e-5
 
 
+def test_oracle_caption_teacher_forced_matches_reference_golden():
+    """MVLBertForImageCaption.encode_forward (model.py:518-550, num_beams=0), both learning strategies."""
+    g = torch.load(os.path.join(GOLDEN, "caption_stress.pt"))
+    sd = _sd("caption", g["weight_seed"], g["flavour"])
+    x, ids = synth.synth_images(g["B"], g["data_seed"], g["img_scale"]), synth.synth_token_ids(g["B"], g["L"], g["data_seed"])
+    for strategy in ("unilm", "normal"):
+        with torch.no_grad():
+            out = O.caption_encode_forward(sd, x, ids, strategy)
+        assert out.shape == (g["B"], 30522, g["L"])
+        _check_taps({"caption_" + strategy: out}, {"caption_" + strategy: g[strategy]})
+
+
 def test_oracle_rank_matrix_matches_reference_golden():
     g = torch.load(os.path.join(GOLDEN, "rank6.pt"))
     sd = _sd("retrieval", g["weight_seed"], "stress")
