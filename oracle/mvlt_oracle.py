@@ -449,6 +449,13 @@ def resnet_flops(layers=RESNET_LAYERS["resnet101"], img: int = 224) -> float:
 def flops_per_pair(L: int = 80, conv: str = "swintransformer") -> float:
     """Algorithmic FLOPs (MAC*2, unpadded) of one Swin-S + BERT-base pair — BASELINE.md §3 (conv="resnet101"/"resnet50":
     the Bottleneck trunk + resnet_fc instead of Swin-S)."""
+    if conv in ("linear", "vit"):              # 196 image tokens: S = 198 + L
+        S = 198 + L
+        bert = 12 * (2 * S * 768 * (3 * 768 + 768 + 2 * 3072) + 2 * 2 * 12 * S * S * 64)
+        trunk = 2 * 196 * 768 * 768
+        if conv == "vit":
+            trunk += 12 * (2 * 197 * 768 * (3 * 768 + 768 + 2 * 3072) + 2 * 2 * 12 * 197 * 197 * 64)
+        return trunk + bert + 2 * 768 * 768 * 2
     if conv in RESNET_LAYERS:
         S = 51 + L
         bert = 12 * (2 * S * 768 * (3 * 768 + 768 + 2 * 3072) + 2 * 2 * 12 * S * S * 64)

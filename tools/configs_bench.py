@@ -80,3 +80,7 @@ if a.only in ("", "config3"):
     pretrain()
 if a.only in ("", "config5"):
     vqa_like("config5 ResNet-101 + BERT-base VQA forward", "resnet101", 64, 80)
+if a.only in ("backbones",):       # the other Conv_layer branches of the reference (model.py:195-228)
+    vqa_like("ResNet-50 + BERT-base VQA forward", "resnet50", 64, 80)
+    vqa_like("linear-patch (196 tokens) + BERT-base VQA forward", "linear", 64, 80)
+    vqa_like("ViT-B/16 (196 tokens) + BERT-base VQA forward", "vit", 64, 80)

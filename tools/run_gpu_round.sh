@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m gpu --timeout 600 2>&1 | tail -25 > gpurun_out/t_all.log
-tail -n 25 gpurun_out/t_all.log | cut -c1-300
+timeout 600 python tools/configs_bench.py --only backbones > gpurun_out/backbones_bench.jsonl 2> gpurun_out/backbones_bench.err
+cut -c1-260 gpurun_out/backbones_bench.jsonl; tail -n 3 gpurun_out/backbones_bench.err
