@@ -337,3 +337,22 @@ def _col_ref(s, l, none):
         hit = np.nonzero(lc[np.argsort(sc, kind="stable")[::-1]] == 1)[0]
         out.append(int(hit[0]) if hit.size else none)
     return out
+
+
+@pytest.mark.parametrize("M,N,K", [(8384, 768, 768), (8384, 768, 3072), (12544, 384, 1536), (12544, 384, 384), (3136, 768, 3072),
+                                   (50176, 192, 768), (8200, 768, 320), (5000, 100, 1024)])
+def test_gemm_tc_inplace_residual_model_shapes(cuda, M, N, K):
+    """In-place residual GEMMs (reduce-add epilogue) at the model's full shapes (BERT attention / FFN outputs, Swin proj / fc2)
+    plus ragged M / N / K and a padded row stride: x + a @ w.T + b, columns beyond N untouched."""
+    from medical_vision_langauge_transformer_b200 import ops
+    a = rnd(M, K, seed=21).bfloat16()
+    w = rnd(N, K, seed=22, scale=1 / math.sqrt(K)).bfloat16()
+    bias = rnd(N, seed=23)
+    ldc = (N + 3) // 4 * 4
+    x0 = rnd(M, ldc, seed=24)
+    x = x0.clone()
+    ops.linear(a, w, bias, residual=x[:, :N], out=x[:, :N])
+    ref = x0[:, :N] + a.float() @ w.float().t() + bias
+    assert relerr(x[:, :N], ref) < 2e-3
+    if ldc > N:
+        assert torch.equal(x[:, N:], x0[:, N:])
