@@ -96,7 +96,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_port_pairs_per_s(batch: int, L: int, min_seconds: float = 10.0, max_runs: int = 12, conv: str = "swintransformer"):
+def cpu_port_pairs_per_s(batch: int, L: int, min_seconds: float = 10.0, max_runs: int = 80, conv: str = "swintransformer"):
     """The reference forward (oracle port, torch fp32) on the host cores: VQA forward on `batch` pairs, repeated."""
     import torch
     from medical_vision_langauge_transformer_b200 import synth
