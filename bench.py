@@ -241,6 +241,72 @@ def gemm_roofline(model, x, ids, pk, steps=3):
             "peak_source": pk["source"] + ", sustained figure", "frac_of_burst_peak": achieved / pk["bf16_burst"]}, by_shape
 
 
+def hbm_kernel_rooflines(model, x, ids, pk):
+    """The memory-bound kernel families of the step against the measured HBM peak (north_star: window attention and LayerNorm
+    as a fraction of HBM bandwidth): every launch of a family in one forward is recorded with its arguments, the launches are
+    replayed back to back as one CUDA graph (their activations are distinct buffers of GBs in total: cold), and
+    achieved = algorithmic bytes (each operand read once, each result written once) / device time."""
+    import torch
+    from medical_vision_langauge_transformer_b200 import ops
+    fams = {"layernorm": ("layernorm", []), "window_attention": ("window_attention", []), "joint_attention": ("joint_attention", [])}
+    orig = {k: getattr(ops, name) for k, (name, _) in fams.items()}
+    mods = [m for m in list(sys.modules.values())
+            if getattr(m, "__name__", "").startswith("medical_vision_langauge_transformer_b200.modules") and hasattr(m, "ops")]
+
+    def recorder(key):
+        def f(*a, **kw):
+            out = orig[key](*a, **kw)
+            fams[key][1].append((a, kw, out))
+            return out
+        return f
+
+    try:
+        for k, (name, _) in fams.items():
+            setattr(ops, name, recorder(k))
+        with torch.no_grad():
+            model(x, ids, None)
+        torch.cuda.synchronize()
+    finally:
+        for k, (name, _) in fams.items():
+            setattr(ops, name, orig[k])
+
+    def nbytes(t):
+        return t.numel() * t.element_size()
+
+    res = {}
+    for key, (name, calls) in fams.items():
+        if not calls:
+            continue
+        total = 0
+        for a, kw, out in calls:
+            outs = out if isinstance(out, tuple) else (out,)
+            total += nbytes(a[0]) + sum(nbytes(o) for o in outs if o is not None)   # a[0]: x / qkv
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st), torch.no_grad():
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                for a, kw, out in calls:
+                    kw2 = dict(kw)
+                    if key != "layernorm":
+                        kw2["out"] = out
+                    elif not isinstance(out, tuple):
+                        kw2["out"] = out
+                    orig[key](*a, **kw2)
+            for _ in range(2):
+                g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(5):
+                g.replay()
+            e1.record(st)
+            st.synchronize()
+        t = e0.elapsed_time(e1) * 1e-3 / 5
+        gbs = total / t / 1e9
+        res[key] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                    "launches_per_step": len(calls), "ms_per_step": t * 1e3, "algorithmic_bytes_per_step": total}
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -325,9 +391,10 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_res, t_e2e, t_e2e_wall = t.tolist()
 
-    roof, by_shape, cpu = None, None, None
+    roof, by_shape, cpu, hbm_kernels = None, None, None, None
     if rank == 0 and not args.no_roofline and args.precision == "bf16" and args.conv == "swintransformer":
         roof, by_shape = gemm_roofline(model, d_imgs[0], d_ids[0], pk)
+        hbm_kernels = hbm_kernel_rooflines(model, d_imgs[0], d_ids[0], pk)
         prof = os.path.join(ROOT, "profiles", "gemm_tc_traffic.json")
         if os.path.exists(prof):
             roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
@@ -359,6 +426,8 @@ def run_ours(args):
                                        "gflop_per_pair": flop_pair / 1e9},
             "clocks": clocks,
         }
+        if hbm_kernels:
+            res["hbm_kernels"] = hbm_kernels
         if roof:
             res["roofline"] = roof
             res["gemm_by_shape"] = {f"{m}x{n}x{k}": {"ms_per_step": round(v[0] * 1e3, 4), "tflops": round(v[1] / v[0] / 1e12, 1), "launches": round(v[2])}

@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_e2e_gpu.py -q -m gpu --timeout 600 -k "full_size" 2>&1 | tail -30 > gpurun_out/t_all.log
-tail -n 30 gpurun_out/t_all.log | cut -c1-250
+timeout 900 python bench.py > gpurun_out/bench_v16.json 2> gpurun_out/bench_v16.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_v16.json')); print(json.dumps(d.get('hbm_kernels'), indent=1)); print(d['value'], d['roofline']['frac'], d['cpu_baseline'])"
+tail -n 3 gpurun_out/bench_v16.err
