@@ -166,17 +166,21 @@ window_attn_warp_kernel(const WinParams p) {
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks)
         ldsm_x4(smem_u32(Qs + wa_off(r0 + (lane & 15), ks * 2 + (lane >> 4))), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+      // The table values are fetched first (L2 latency: the kernel's largest single stall when the accumulators were
+      // initialised from them), the MMAs run on zeroed accumulators meanwhile and the table is added afterwards; the two
+      // k-steps are issued as two passes over the seven key tiles so that consecutive HMMAs never share an accumulator.
+      float4 b4[7];
+#pragma unroll
+      for (int nt = 0; nt < 7; ++nt) b4[nt] = __ldg(bt + (mt * 7 + nt) * 32);
       float s[7][4];
 #pragma unroll
-      for (int nt = 0; nt < 7; ++nt) {
-        const float4 b4 = __ldg(bt + (mt * 7 + nt) * 32);
-        s[nt][0] = b4.x; s[nt][1] = b4.y; s[nt][2] = b4.z; s[nt][3] = b4.w;
-      }
+      for (int nt = 0; nt < 7; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < 7; ++nt) {
-        mma_bf16_16816(s[nt], qa[0][0], qa[0][1], qa[0][2], qa[0][3], kf[nt][0], kf[nt][1]);
-        mma_bf16_16816(s[nt], qa[1][0], qa[1][1], qa[1][2], qa[1][3], kf[nt][2], kf[nt][3]);
-      }
+      for (int nt = 0; nt < 7; ++nt) mma_bf16_16816(s[nt], qa[0][0], qa[0][1], qa[0][2], qa[0][3], kf[nt][0], kf[nt][1]);
+#pragma unroll
+      for (int nt = 0; nt < 7; ++nt) mma_bf16_16816(s[nt], qa[1][0], qa[1][1], qa[1][2], qa[1][3], kf[nt][2], kf[nt][3]);
+#pragma unroll
+      for (int nt = 0; nt < 7; ++nt) { s[nt][0] += b4[nt].x; s[nt][1] += b4[nt].y; s[nt][2] += b4[nt].z; s[nt][3] += b4[nt].w; }
       float mx0 = s[0][0], mx1 = s[0][2];
 #pragma unroll
       for (int nt = 0; nt < 7; ++nt) {

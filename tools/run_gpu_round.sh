@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python bench.py > gpurun_out/bench_v16.json 2> gpurun_out/bench_v16.err
-python -c "
-import json; d=json.load(open('gpurun_out/bench_v16.json')); print(json.dumps(d.get('hbm_kernels'), indent=1)); print(d['value'], d['roofline']['frac'], d['cpu_baseline'])"
-tail -n 3 gpurun_out/bench_v16.err
+timeout 600 python -m pytest tests -q -m gpu --timeout 600 -x -k "window or joint or golden" 2>&1 | tail -3 > gpurun_out/t_all.log
+timeout 300 python tools/attn_sweep.py > gpurun_out/attn_sweep.log 2>&1
+tail -n 2 gpurun_out/t_all.log; cat gpurun_out/attn_sweep.log
