@@ -87,6 +87,13 @@ int mvlt_swin_mlp_fused(float* x, long long ldx, const float* gamma, const float
                         const float* b1, const void* w2, const float* b2, long long M, int C, int hidden,
                         mvlt_stream_t stream);
 
+/* LayerNorm + Linear in one tcgen05 kernel (A-stationary): out[M, N] (bf16, row stride ldc) = act(LayerNorm(x; gamma, beta,
+ * eps) . w^T + bias).  x fp32 [M, C] (row stride ldx), w bf16 [N, C], bias fp32 [N] or NULL, act NONE | GELU.  The 128 normalised
+ * rows of a CTA stay in shared memory as the MMA A operand while the N columns stream by.  Replaces vfe.py:356 + :231
+ * (norm1 -> qkv) and vfe.py:385 + :136 (norm2 -> fc1 -> GELU).  C in {192, 384}, N % 32 == 0. */
+int mvlt_ln_linear_bf16(const float* x, long long ldx, const float* gamma, const float* beta, float eps, const void* w,
+                        const float* bias, void* out, long long ldc, long long M, int C, int N, int act, mvlt_stream_t stream);
+
 /* Same contract as mvlt_gemm_bf16_tc in fp32 on the CUDA cores (parity mode, 1e-4 vs the reference); all five
  * activation codes, fp32 residual. */
 int mvlt_gemm_f32_simt(const float* A, long long lda, const float* W, long long ldw, float* C, long long ldc,

@@ -394,6 +394,214 @@ static int launch_swin_mlp(const MlpParams& p, const void* w1, const void* w2, c
   return e == cudaSuccess ? MVLT_OK : (int)e;
 }
 
+// =====================================================================================================================
+// LayerNorm + Linear in one kernel (A-stationary):  out[M, N] (bf16) = act( LayerNorm(x)[M, C] . W[N, C]^T + bias )
+//
+//     vfe.py:356 + :231 (norm1 -> qkv) and vfe.py:385 + :136 (norm2 -> fc1 + erf-GELU) of a Swin block.
+//
+// One CTA owns 128 token rows: sixteen warps LayerNorm them (fp32 statistics) straight into shared memory as the K-major
+// SWIZZLE_128B A operand (the same prologue as the fused MLP above), where they STAY while the output columns are walked in
+// 256-wide chunks: W tiles [256, 64] stream through a TMA ring, tcgen05.mma (M = 128, N = 256) accumulates a chunk in one
+// of two TMEM buffers, and the sixteen epilogue warps drain the other one (tcgen05.ld -> + bias -> erf-GELU -> bf16 ->
+// swizzled staging -> TMA store).  Against LayerNorm kernel + GEMM this removes the bf16 LayerNorm output round trip
+// (4C B/row), one launch, and the GEMM's re-read of A per N tile.
+// =====================================================================================================================
+constexpr int LG_BM = 128, LG_NB = 256, LG_EPI_WARPS = 16, LG_THREADS = (2 + LG_EPI_WARPS) * 32;
+constexpr int LG_SLOT = LG_NB * 128;   // one W tile: [256 rows, 64 k] bf16 = 32 KB
+
+template <int C> struct LnGemmPlan {
+  static_assert(C == 192 || C == 384, "row widths whose A operand stays resident (Swin-S stages 1 and 2)");
+  static constexpr int KB1 = C / 64;
+  static constexpr int A1_BYTES = KB1 * LG_BM * 128;
+  static constexpr int STAGING_BYTES = LG_EPI_WARPS * 2048;
+  static constexpr int AUX_BYTES = 512;
+  static constexpr int NSLOT_RAW = (227 * 1024 - 1024 - AUX_BYTES - A1_BYTES - STAGING_BYTES) / LG_SLOT;
+  static constexpr int NSLOT = NSLOT_RAW > 4 ? 4 : NSLOT_RAW;
+  static constexpr int SMEM_BYTES = A1_BYTES + NSLOT * LG_SLOT + STAGING_BYTES + AUX_BYTES + 1024;
+  static_assert(NSLOT >= 3 && SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+struct LnGemmParams {
+  MlpParams ln;        // x, ldx, M, gamma, beta, eps (b1 / b2 unused)
+  const float* bias;   // [N] or nullptr
+  int N;
+};
+
+template <int C, int ACT>
+__global__ void __launch_bounds__(LG_THREADS, 1)
+ln_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out, LnGemmParams p) {
+  using P = LnGemmPlan<C>;
+  constexpr int KB1 = P::KB1, NSLOT = P::NSLOT;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* a1 = smem;
+  uint8_t* ring = a1 + P::A1_BYTES;
+  uint8_t* staging = ring + NSLOT * LG_SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + P::STAGING_BYTES);
+  uint64_t* w_full = bars;               // [NSLOT] TMA -> MMA
+  uint64_t* w_empty = w_full + NSLOT;    // [NSLOT] MMA -> TMA
+  uint64_t* a1_full = w_empty + NSLOT;   // LayerNorm warps -> MMA (16 arrivals)
+  uint64_t* acc_full = a1_full + 1;      // [2] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;    // [2] epilogue -> MMA (16 arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = (long long)blockIdx.x * LG_BM;
+  const int n_chunks = (p.N + LG_NB - 1) / LG_NB;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_out);
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    mbar_init(a1_full, LG_EPI_WARPS);
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], LG_EPI_WARPS); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer: weights only (static: no griddepcontrol.wait) ------------------
+    uint32_t cnt = 0;
+    for (int nc = 0; nc < n_chunks; ++nc)
+      for (int kb = 0; kb < KB1; ++kb, ++cnt) {
+        const uint32_t s = cnt % NSLOT, ph = (cnt / NSLOT) & 1;
+        mbar_wait(&w_empty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&w_full[s], LG_SLOT);          // rows beyond N arrive as zeros, the byte count is the box
+          tma_load_2d(ring + s * LG_SLOT, &tmap_w, &w_full[s], kb * 64, nc * LG_NB);
+        }
+        __syncwarp();
+      }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ------------------------------------------------------------------
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const uint32_t idesc = umma_idesc_bf16(LG_BM, LG_NB);
+    const uint64_t desc_a1 = umma_desc_k_sw128(smem_u32(a1));
+    const uint64_t desc_w = umma_desc_k_sw128(smem_u32(ring));
+    mbar_wait(a1_full, 0);
+    tc_fence_after();
+    uint32_t cnt = 0;
+    for (int nc = 0; nc < n_chunks; ++nc) {
+      const int b = nc & 1, u = nc >> 1;
+      mbar_wait(&acc_empty[b], (u & 1) ^ 1);                   // the epilogue has drained this buffer (chunk nc - 2)
+      tc_fence_after();
+      const uint32_t d = tmem_base + b * LG_NB;
+      for (int kb = 0; kb < KB1; ++kb, ++cnt) {
+        const uint32_t s = cnt % NSLOT, ph = (cnt / NSLOT) & 1;
+        mbar_wait(&w_full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d, desc_a1 + (uint64_t)(kb * (LG_BM * 128 >> 4) + 2 * k), desc_w + (uint64_t)(s * (LG_SLOT >> 4) + 2 * k),
+                      idesc, (kb | k) != 0);
+          umma_commit(&w_empty[s]);
+          if (kb == KB1 - 1) umma_commit(&acc_full[b]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------- LayerNorm prologue, then epilogue (warps 2-17) -------------------------------
+    const int ew = warp - 2;
+    const int quarter = warp & 3;  // TMEM lanes [32 quarter, +32)
+    const int part = ew >> 2;      // this warp's 32-column chunks of a 256-column buffer: part, part + 4
+    pdl_grid_sync();               // x is written by the previous kernel
+    mlp_ln_rows<C, LG_BM / LG_EPI_WARPS>(p.ln, row0, a1, ew, lane);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a1_full);
+
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint8_t* sb = staging + ew * 2048;
+    const uint32_t row_base = (uint32_t)lane * 64u, swz = ((uint32_t)lane >> 1) & 3u;   // 64 B rows, SWIZZLE_64B
+    const int m0 = (int)row0 + quarter * 32;
+#pragma unroll 1
+    for (int nc = 0; nc < n_chunks; ++nc) {
+      const int b = nc & 1, u = nc >> 1;
+      mbar_wait(&acc_full[b], u & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = part; c < LG_NB / 32; c += LG_EPI_WARPS / 4) {
+        const int n0 = nc * LG_NB + c * 32;
+        if (n0 >= p.N) break;                                   // warp-uniform; N % 32 == 0
+        uint32_t rg[32];
+        tmem_ld_32x32(tmem_lane + b * LG_NB + c * 32, rg);
+        float4 bv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          bv[i] = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        tmem_ld_wait();
+        float2 v[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[2 * i] = add2(make_float2(__uint_as_float(rg[4 * i]), __uint_as_float(rg[4 * i + 1])), make_float2(bv[i].x, bv[i].y));
+          v[2 * i + 1] = add2(make_float2(__uint_as_float(rg[4 * i + 2]), __uint_as_float(rg[4 * i + 3])), make_float2(bv[i].z, bv[i].w));
+        }
+        if (ACT == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = gelu_erf_pk2(v[i]);
+        }
+        if (elect_one()) bulk_wait_read<0>();                   // this warp's previous store has left the staging buffer
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(sb + row_base + (((uint32_t)j ^ swz) << 4)) =
+              make_uint4(pack_bf16x2(v[4 * j].x, v[4 * j].y), pack_bf16x2(v[4 * j + 1].x, v[4 * j + 1].y),
+                         pack_bf16x2(v[4 * j + 2].x, v[4 * j + 2].y), pack_bf16x2(v[4 * j + 3].x, v[4 * j + 3].y));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+          tma_store_2d(&tmap_out, sb, n0, m0);                  // rows beyond M are clipped by the TMA unit
+          bulk_commit();
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);
+    }
+    if (elect_one()) bulk_wait_all();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int C, int ACT>
+static int launch_ln_linear(const LnGemmParams& p, const void* w, void* out, long long ldc, cudaStream_t stream) {
+  using P = LnGemmPlan<C>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ln_linear_kernel<C, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  CUtensorMap tw, to;
+  int rc;
+  if ((rc = make_tmap(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, p.N, C, C, 64, LG_NB, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != MVLT_OK) return rc;
+  if ((rc = make_tmap(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, p.ln.M, p.N, ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B,
+                      CU_TENSOR_MAP_L2_PROMOTION_NONE)) != MVLT_OK) return rc;
+  const long long tiles = (p.ln.M + LG_BM - 1) / LG_BM;
+  cudaError_t e = launch_k(ln_linear_kernel<C, ACT>, dim3((unsigned)tiles), dim3(LG_THREADS), (size_t)P::SMEM_BYTES, stream, tw, to, p);
+  return e == cudaSuccess ? MVLT_OK : (int)e;
+}
+
 }  // namespace mvlt
 
 using namespace mvlt;
@@ -423,4 +631,23 @@ extern "C" int mvlt_swin_mlp_fused(float* x, long long ldx, const float* gamma, 
     case 192: return launch_swin_mlp<192>(p, w1, w2, stream);
     default: return launch_swin_mlp<384>(p, w1, w2, stream);
   }
+}
+
+extern "C" int mvlt_ln_linear_bf16(const float* x, long long ldx, const float* gamma, const float* beta, float eps, const void* w,
+                                   const float* bias, void* out, long long ldc, long long M, int C, int N, int act,
+                                   cudaStream_t stream) {
+  if (!x || !gamma || !beta || !w || !out || M <= 0 || N <= 0) return MVLT_ERR_INVALID;
+  if ((C != 192 && C != 384) || N % 32 != 0 || (act != 0 && act != 1)) return MVLT_ERR_UNSUPPORTED;
+  if (ldx < C || ldx % 4 != 0 || ldc < N || ldc % 8 != 0) return MVLT_ERR_INVALID;
+  if (((uintptr_t)x & 15) || ((uintptr_t)w & 15) || ((uintptr_t)out & 15) || ((uintptr_t)gamma & 15) || ((uintptr_t)beta & 15) ||
+      (bias && ((uintptr_t)bias & 15))) return MVLT_ERR_INVALID;
+  if ((M + LG_BM - 1) / LG_BM > 0x7fffffffLL || M > 0x7fffffffLL) return MVLT_ERR_INVALID;
+  int rc = mvlt_gemm_tc_init();
+  if (rc != MVLT_OK) return rc;
+  LnGemmParams p;
+  p.ln.x = const_cast<float*>(x); p.ln.ldx = ldx; p.ln.M = M; p.ln.gamma = gamma; p.ln.beta = beta; p.ln.b1 = nullptr; p.ln.b2 = nullptr;
+  p.ln.eps = eps; p.ln.trace = nullptr;
+  p.bias = bias; p.N = N;
+  if (C == 384) return act ? launch_ln_linear<384, 1>(p, w, out, ldc, stream) : launch_ln_linear<384, 0>(p, w, out, ldc, stream);
+  return act ? launch_ln_linear<192, 1>(p, w, out, ldc, stream) : launch_ln_linear<192, 0>(p, w, out, ldc, stream);
 }

@@ -250,6 +250,12 @@ class SwinTransformer(nn.Module):
         # (profiles/r01_fused_mlp_vs_chain.log), "96,192,384" enables it everywhere, "" nowhere.
         fused_widths = tuple(int(v) for v in os.environ.get("MVLT_FUSED_MLP", "96").split(",") if v.strip()) \
             if self.precision == "bf16" else ()
+        # LayerNorm + Linear as ONE A-stationary tcgen05 kernel (norm1 -> qkv, norm2 -> fc1 + GELU) for the widths listed in
+        # MVLT_FUSED_LN_LINEAR (bf16 mode).  Default: none — at C = 384 it removes 36 LayerNorm launches but runs 29.9 us per
+        # call against 29-33 us for LayerNorm + GEMM (98 row tiles on 148 SMs, N = 256 chunks fed from shared memory at ~70 %
+        # of the tensor rate): 13.87 k vs 14.00 k pairs/s for the step (profiles/r01_ln_linear_fused_experiment.log).
+        ln_lin_widths = tuple(int(v) for v in os.environ.get("MVLT_FUSED_LN_LINEAR", "").split(",") if v.strip()) \
+            if self.precision == "bf16" else ()
         taps = self.taps
         if taps is not None:
             taps["patch_embed"] = X.clone().view(B, -1, X.shape[-1])
@@ -261,16 +267,23 @@ class SwinTransformer(nn.Module):
             for i, blk in enumerate(layer.blocks):
                 w = pk["blocks"][bi]
                 bi += 1
+                ln_lin = C in ln_lin_widths and C in ops.FUSED_LN_LINEAR_WIDTHS
                 if a_first is not None:
                     a, a_first = a_first, None
+                    qkv = ops.linear(a, w["qkv_w"], w["qkv_b"])
+                elif ln_lin:
+                    qkv = ops.ln_linear(X, w["n1w"], w["n1b"], blk.norm1.eps, w["qkv_w"], w["qkv_b"])
                 else:
                     a = ops.layernorm(X, w["n1w"], w["n1b"], blk.norm1.eps, adt)
-                qkv = ops.linear(a, w["qkv_w"], w["qkv_b"])
+                    qkv = ops.linear(a, w["qkv_w"], w["qkv_b"])
                 o = ops.window_attention(qkv, w["relbias"], B, H, W, C, blk.num_heads, blk.window_size, blk.shift_size,
                                          blk.attn.scale)
                 ops.linear(o, w["proj_w"], w["proj_b"], residual=X, out=X)
                 if C in fused_widths and C in ops.FUSED_MLP_WIDTHS and w["fc1_w"].shape[0] == 4 * C:
                     ops.swin_mlp(X, w["n2w"], w["n2b"], blk.norm2.eps, w["fc1_w"], w["fc1_b"], w["fc2_w"], w["fc2_b"])
+                elif ln_lin:
+                    h = ops.ln_linear(X, w["n2w"], w["n2b"], blk.norm2.eps, w["fc1_w"], w["fc1_b"], act=ops.ACT_GELU)
+                    ops.linear(h, w["fc2_w"], w["fc2_b"], residual=X, out=X)
                 else:
                     a = ops.layernorm(X, w["n2w"], w["n2b"], blk.norm2.eps, adt)
                     h = ops.linear(a, w["fc1_w"], w["fc1_b"], act=ops.ACT_GELU)

@@ -170,6 +170,25 @@ def swin_mlp(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: floa
     return x
 
 
+FUSED_LN_LINEAR_WIDTHS = (192, 384)
+
+
+def ln_linear(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, w: torch.Tensor,
+              bias: Optional[torch.Tensor], act: int = ACT_NONE) -> torch.Tensor:
+    """act(layernorm(x) @ w.T + bias) -> bf16 [M, N] in one kernel (fp32 x [M, C], bf16 w [N, C], C in FUSED_LN_LINEAR_WIDTHS)."""
+    lib = _lib.ensure_init()
+    M, C, ldx = _rows2d(x)
+    N = w.shape[0]
+    assert x.dtype == torch.float32 and w.dtype == torch.bfloat16 and w.shape == (N, C) and w.is_contiguous()
+    for t, n in ((gamma, C), (beta, C)) + (((bias, N),) if bias is not None else ()):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n
+    out = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
+    rc = lib.mvlt_ln_linear_bf16(x.data_ptr(), ldx, gamma.data_ptr(), beta.data_ptr(), float(eps), w.data_ptr(), _ptr(bias),
+                                 out.data_ptr(), N, M, C, N, act, _stream())
+    _lib.check(rc, f"mvlt_ln_linear_bf16(M={M},C={C},N={N})")
+    return out
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out_dtype: torch.dtype,
               gelu: bool = False, out: Optional[torch.Tensor] = None, bf16_copy: bool = False):
     """LayerNorm rows.  bf16_copy=True additionally returns the rows rounded to bf16 (-> (out, copy))."""

@@ -356,3 +356,24 @@ def test_gemm_tc_inplace_residual_model_shapes(cuda, M, N, K):
     assert relerr(x[:, :N], ref) < 2e-3
     if ldc > N:
         assert torch.equal(x[:, N:], x0[:, N:])
+
+
+@pytest.mark.parametrize("C,N,act", [(384, 1152, 0), (384, 1536, 1), (192, 576, 0), (192, 768, 1), (384, 384, 1), (192, 96, 0)])
+@pytest.mark.parametrize("M", [12544, 300, 1, 129])
+def test_ln_linear_fused(cuda, C, N, act, M):
+    """LayerNorm + Linear (+ erf-GELU) in one A-stationary tcgen05 kernel vs (a) torch in fp32 on the bf16-rounded LayerNorm
+    output and (b) the unfused LayerNorm kernel + GEMM chain; full tiles, ragged M, a single row, every N chunking
+    (1152 = 4.5 x 256, 1536 = 6 x 256, one partial chunk)."""
+    from medical_vision_langauge_transformer_b200 import ops
+    x = rnd(M, C, seed=31) * 1.5 + 0.3
+    g, b = 1 + rnd(C, seed=32, scale=0.1), rnd(C, seed=33, scale=0.05)
+    w = rnd(N, C, seed=34, scale=1 / math.sqrt(C)).bfloat16()
+    bias = rnd(N, seed=35, scale=0.2)
+    out = ops.ln_linear(x, g, b, 1e-5, w, bias, act=act)
+    a = F.layer_norm(x, (C,), g, b, 1e-5).bfloat16().float()
+    ref = a @ w.float().t() + bias
+    ref = F.gelu(ref) if act else ref
+    assert out.dtype == torch.bfloat16 and out.shape == (M, N)
+    assert relerr(out, ref) < 1e-2
+    chain = ops.linear(ops.layernorm(x, g, b, 1e-5, torch.bfloat16), w, bias, act=act)
+    assert relerr(out, chain) < 1e-2
