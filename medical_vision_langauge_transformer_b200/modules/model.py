@@ -448,8 +448,8 @@ class MVLBertForPretraining(_PackedMixin, MVLBertPretrainedModel):
 class MVLBertForImageCaption(_PackedMixin, MVLBertPretrainedModel):
     """model.py:479-550: report generation / image captioning.  `forward(image, caption, num_beams=0, learning_strategy)` is the
     teacher-forced pass (`encode_forward`, model.py:518-550: seq2seq mask, MLM head over the text positions ('unilm') or over
-    [SEP], t1..t(n-1) ('normal')) -> logits [B, vocab, L] as in the reference.  Greedy / beam search (num_beams >= 1) decode
-    through the KV-cache branch of `get_embedding` (model.py:82-108), which is outside the accelerated path."""
+    [SEP], t1..t(n-1) ('normal')) -> logits [B, vocab, L] as in the reference.  `num_beams=1` is greedy decoding (`greedy_search`,
+    by prefix recompute on the forward kernels); beam search (`num_beams > 1`) is outside the accelerated path."""
 
     def __init__(self, config, tokenizer=None):
         super().__init__(config)
@@ -470,23 +470,69 @@ class MVLBertForImageCaption(_PackedMixin, MVLBertPretrainedModel):
                     lw=f32(p.transform.LayerNorm.weight), lb=f32(p.transform.LayerNorm.bias),
                     dw=p.decoder.weight.detach().to(wd).contiguous(), db=f32(p.decoder.bias))
 
+    def _mlm_logits(self, rows):
+        """BertOnlyMLMHead (HF modeling_bert.py:488-512) on [n, D] rows in the GEMM operand dtype -> fp32 logits [n, vocab]."""
+        w = self.packed()
+        t = ops.linear(rows, w["tw"], w["tb"], act=ops.ACT_GELU, out_dtype=torch.float32)
+        t = ops.layernorm(t, w["lw"], w["lb"], self.config.layer_norm_eps, act_dtype(self.precision))
+        V = w["dw"].shape[0]
+        ld = (V + 31) // 32 * 32
+        logits = torch.empty((rows.shape[0], ld), device=t.device, dtype=torch.float32)[:, :V]
+        ops.linear(t, w["dw"], w["db"], out=logits)
+        return logits
+
     def forward(self, image, caption, num_beams=0, learning_strategy="unilm", sample_mode="greedy"):
-        if num_beams >= 1:
-            raise NotImplementedError("greedy / beam search decode (model.py:636-984, KV-cache branch of get_embedding) is "
-                                      "outside the accelerated forward path; num_beams=0 runs the teacher-forced pass")
+        if num_beams > 1:
+            raise NotImplementedError("beam search decode (model.py:636-824) is outside the accelerated forward path; "
+                                      "num_beams=0 runs the teacher-forced pass, num_beams=1 greedy decoding")
         if learning_strategy not in ("unilm", "normal"):
             raise NotImplementedError("learning_strategy:", learning_strategy, "is not implemented! Try 'unilm' or 'normal'.")
+        if num_beams == 1:
+            return self.greedy_search(self.conv(image), learning_strategy=learning_strategy, sample_mode=sample_mode)
         feat, hidden, shadow, B, S = self._trunk(image, caption, None, True)
         n_obj, L, D = feat.shape[1], caption.shape[1], hidden.shape[1]
         # 'unilm': hidden states of t1..tn ; 'normal': [SEP], t1..t(n-1) = the same window shifted one row up (model.py:536-544)
         first = n_obj + 2 if learning_strategy == "unilm" else n_obj + 1
         src = shadow if shadow is not None else hidden
         rows = src.view(B, S, D)[:, first:first + L].reshape(B * L, D)
-        w = self.packed()
-        t = ops.linear(rows, w["tw"], w["tb"], act=ops.ACT_GELU, out_dtype=torch.float32)
-        t = ops.layernorm(t, w["lw"], w["lb"], self.config.layer_norm_eps, act_dtype(self.precision))
-        V = w["dw"].shape[0]
-        ld = (V + 31) // 32 * 32
-        logits = torch.empty((B * L, ld), device=t.device, dtype=torch.float32)[:, :V]
-        ops.linear(t, w["dw"], w["db"], out=logits)
-        return logits.view(B, L, V).transpose(1, 2)          # batch, vocab_size, seq_len (model.py:534)
+        V = self.packed()["dw"].shape[0]
+        return self._mlm_logits(rows).view(B, L, V).transpose(1, 2)          # batch, vocab_size, seq_len (model.py:534)
+
+    @torch.no_grad()
+    def greedy_search(self, image_feature, learning_strategy="unilm", sample_mode="greedy", max_length=None,
+                      pad_token_id=None, eos_token_id=None, mask_token_id=None):
+        """model.py:826-984 with `learning_strategy='unilm'`, `sample_mode='greedy'`: every step feeds the tokens generated so
+        far plus one [MASK] and takes the argmax of the MLM head at the [MASK] position; finished rows emit `pad`; stops when
+        every row has produced [END] or at `max_length`.  -> (input_ids [B, steps], concatenated per-step max logits).
+
+        The reference decodes incrementally through HF's KV cache (two new tokens per step, the [MASK] entry trimmed from the
+        cache afterwards, model.py:890-894).  Under the seq2seq mask every cached key/value is exactly what a forward over
+        the whole prefix recomputes, so this implementation RE-RUNS the joint encoder over the growing prefix each step on the
+        forward kernels (image features computed once): same arithmetic, O(L^2) instead of O(L) token-forwards."""
+        if learning_strategy != "unilm" or sample_mode != "greedy":
+            raise NotImplementedError("only learning_strategy='unilm' with sample_mode='greedy' decodes on the accelerated path")
+        cfg = self.config
+        max_length = max_length if max_length is not None else cfg.max_length
+        pad = pad_token_id if pad_token_id is not None else (cfg.pad_token_id if cfg.pad_token_id is not None else 0)
+        eos = eos_token_id if eos_token_id is not None else cfg.eos_token_id
+        mask_id = mask_token_id if mask_token_id is not None else \
+            (self.tokenizer.mask_token_id if self.tokenizer is not None else cfg.mask_token_id)
+        B, dev = image_feature.shape[0], image_feature.device
+        unfinished = torch.ones(B, dtype=torch.int64, device=dev)
+        mask_col = torch.full((B, 1), mask_id, dtype=torch.int64, device=dev)
+        input_ids, probs = None, []
+        for _ in range(max_length):
+            text = mask_col if input_ids is None else torch.cat([input_ids, mask_col], dim=-1)
+            hidden, shadow, _, S = self.MVLBert.encode(text.contiguous(), None, image_feature, None, True)
+            src = shadow if shadow is not None else hidden
+            logits = self._mlm_logits(src.view(B, S, -1)[:, -1])                 # hidden state of the [MASK] position
+            scores, tokens = torch.max(logits, dim=-1)
+            if eos is not None:
+                tokens = tokens * unfinished + pad * (1 - unfinished)
+            input_ids = tokens[:, None] if input_ids is None else torch.cat([input_ids, tokens[:, None]], dim=-1)
+            if eos is not None:
+                unfinished = unfinished * (tokens != eos).long()
+            if unfinished.max() == 0:
+                break
+            probs.append(scores)
+        return input_ids, (torch.cat(probs, dim=-1) if probs else torch.empty(0, device=dev))

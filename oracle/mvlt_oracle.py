@@ -386,6 +386,36 @@ def caption_encode_forward(sd: SD, image: Tensor, caption: Tensor, learning_stra
     return F.linear(t, sd[p + "decoder.weight"], sd[p + "decoder.bias"]).transpose(1, 2)
 
 
+def caption_greedy_decode(sd: SD, image: Tensor, max_length: int, mask_id: int = 103, eos_id: int = 104, pad_id: int = 0):
+    """model.py:826-984 (`greedy_search`, learning_strategy='unilm', sample_mode='greedy') restated WITHOUT the KV cache: each
+    step runs the joint encoder over [t1..tk, [MASK]] with the seq2seq mask and takes the argmax of the MLM head at the [MASK]
+    position (:881-897); finished rows emit pad (:935); the [MASK] entry never enters the next step's context (:890-894 trims
+    it from the cache), which is exactly what re-encoding the prefix does.  NOTE: the reference's own decode loop does not run
+    under the installed transformers 5.5 (BertEncoder no longer returns tuple caches), so this function is pinned only by
+    its agreement with `caption_encode_forward` (teacher-forced logits at the same positions) — "parity unpinned" for decode.
+    -> (input_ids [B, steps], per-step max logits as the reference concatenates them, list of per-step top-2 margins)."""
+    feat = conv_layer(sd, image)
+    B = feat.shape[0]
+    p = "MLM_head_seq2seq.predictions."
+    unfinished = torch.ones(B, dtype=torch.int64)
+    mask_col = torch.full((B, 1), mask_id, dtype=torch.int64)
+    input_ids, probs, margins = None, [], []
+    for _ in range(max_length):
+        text = mask_col if input_ids is None else torch.cat([input_ids, mask_col], -1)
+        h, _ = mvlbert(sd, text, feat, seq2seq=True)
+        logits = F.linear(head_transform(sd, p + "transform.", h[:, -1]), sd[p + "decoder.weight"], sd[p + "decoder.bias"])
+        top2 = logits.topk(2, -1).values
+        margins.append(top2[:, 0] - top2[:, 1])
+        scores, tokens = logits.max(-1)
+        tokens = tokens * unfinished + pad_id * (1 - unfinished)
+        input_ids = tokens[:, None] if input_ids is None else torch.cat([input_ids, tokens[:, None]], -1)
+        unfinished = unfinished * (tokens != eos_id).long()
+        if unfinished.max() == 0:
+            break
+        probs.append(scores)
+    return input_ids, (torch.cat(probs, -1) if probs else torch.empty(0)), margins
+
+
 # ----------------------------------------------------------------------------------------------
 # N x N retrieval scoring and ranking
 # ----------------------------------------------------------------------------------------------

@@ -115,6 +115,22 @@ def test_oracle_caption_teacher_forced_matches_reference_golden():
         _check_taps({"caption_" + strategy: out}, {"caption_" + strategy: g[strategy]})
 
 
+def test_oracle_greedy_decode_is_consistent_with_teacher_forced_pass():
+    """The reference's decode loop does not run under transformers 5.5 (no goldens possible), so the decode restatement is tied
+    to the golden-pinned teacher-forced function: under the seq2seq mask, step k of greedy decoding = the 'unilm' logits at
+    text position k of a teacher-forced pass over [t1..t(k-1), [MASK]] (later positions cannot influence it)."""
+    sd = _sd("caption", 0, "stress")
+    x = synth.synth_images(1, 61, 1.0)
+    steps = 3
+    with torch.no_grad():
+        ids, scores, _ = O.caption_greedy_decode(sd, x, steps)
+        for k in range(steps):
+            caption = torch.cat([ids[:, :k], torch.full((1, 1), 103), torch.zeros(1, steps - k - 1, dtype=torch.long)], 1)
+            logits = O.caption_encode_forward(sd, x, caption, "unilm")[:, :, k]          # [1, vocab]
+            assert logits.argmax(-1).item() == ids[0, k].item()
+            assert abs(logits.max().item() - scores[k].item()) < 1e-4
+
+
 def test_oracle_rank_matrix_matches_reference_golden():
     g = torch.load(os.path.join(GOLDEN, "rank6.pt"))
     sd = _sd("retrieval", g["weight_seed"], "stress")
