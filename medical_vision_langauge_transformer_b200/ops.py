@@ -77,7 +77,7 @@ def conv_out_hw(H: int, W: int, R: int, S: int, stride: int, pad: int):
 
 def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], B: int, H: int, W: int, R: int, S: int,
                 stride: int, pad: int, act: int = ACT_NONE, residual: Optional[torch.Tensor] = None,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, block_n: int = 0) -> torch.Tensor:
     """Conv2d (+ folded BatchNorm bias, + identity, + ReLU) over the NHWC activation x [B*H*W, C] -> [B*Ho*Wo, N].
     w [N, R*S*C] tap-major (k = (ky*S + kx)*C + c).  bf16: implicit GEMM, A fetched by im2col-mode TMA inside the tcgen05
     kernel; fp32 (parity mode): explicit patch matrix + CUDA-core GEMM."""
@@ -106,7 +106,7 @@ def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
     rc = lib.mvlt_conv2d_nhwc_bf16_tc(x.data_ptr(), B, H, W, C, w.data_ptr(), ldw, out.data_ptr(), ldc, _ptr(bias),
-                                      _ptr(residual), ldres, N, R, S, stride, pad, act, 0, _stream())
+                                      _ptr(residual), ldres, N, R, S, stride, pad, act, block_n, _stream())
     _lib.check(rc, f"mvlt_conv2d_nhwc_bf16_tc(B={B},H={H},W={W},C={C},N={N},k={R}x{S},s={stride})")
     return out
 
