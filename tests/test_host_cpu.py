@@ -28,6 +28,28 @@ def test_cabi_library_loads_and_exports_every_declared_symbol():
     assert declared <= exported
 
 
+def test_header_is_plain_c_and_links_from_a_c_host(tmp_path):
+    """include/mvlt_b200.h is the binding a non-Python host compiles against: a C11 translation unit that takes the address
+    of every declared entry point must compile with gcc (no C++, no CUDA headers) and link against libmvlt_b200.so; it runs
+    without a GPU (only mvlt_abi_version is called)."""
+    from medical_vision_langauge_transformer_b200 import _lib
+    _lib.load()
+    header = open(os.path.join(ROOT, "include", "mvlt_b200.h")).read()
+    names = sorted(set(re.findall(r"^int (mvlt_\w+)\(", header, flags=re.M)))
+    src = tmp_path / "host.c"
+    src.write_text('#include <stdio.h>\n#include "mvlt_b200.h"\ntypedef void (*fn_t)(void);\nint main(void) {\n  fn_t fns[] = {'
+                   + ", ".join(f"(fn_t){n}" for n in names)
+                   + '};\n  printf("%d %d\\n", (int)(sizeof fns / sizeof fns[0]), mvlt_abi_version());\n  return fns[0] == 0;\n}\n')
+    exe = tmp_path / "host"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = ["gcc", "-std=c11", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", libdir, "-l:libmvlt_b200.so", f"-Wl,-rpath,{libdir}", "-Wl,-rpath,/usr/local/cuda/lib64", "-L/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == [str(len(names)), "1"], (out.stdout, out.stderr)
+
+
 def test_ops_fail_loudly_without_a_gpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
