@@ -482,6 +482,8 @@ using namespace mvlt;
 template <int NCH> constexpr int joint_flash_smem() { return 48 * NCH * 64 * 2 * 2 + 3 * 16 * 64 * 2 + 48 * NCH * 4; }
 
 extern "C" int mvlt_attn_init(void) {
+  static unsigned long long devices = 0;
+  if (!first_use_on_device(devices)) return MVLT_OK;
   int rc;
   if ((rc = set_smem(joint_attn_flash_kernel<2>, joint_flash_smem<2>())) != MVLT_OK) return rc;
   if ((rc = set_smem(joint_attn_flash_kernel<3>, joint_flash_smem<3>())) != MVLT_OK) return rc;
@@ -498,6 +500,7 @@ extern "C" int mvlt_attn_init(void) {
 extern "C" int mvlt_window_attention(const void* qkv, void* out, int dtype, const float* relbias, int B, int H, int W,
                                      int C, int heads, int window, int shift, float scale, cudaStream_t stream) {
   if (!qkv || !out || !relbias || B <= 0 || heads <= 0 || C != heads * 32) return MVLT_ERR_INVALID;
+  { const int rc0 = mvlt_attn_init(); if (rc0 != MVLT_OK) return rc0; }
   if (window != 7 || H % window || W % window || shift < 0 || shift >= window) return MVLT_ERR_UNSUPPORTED;
   AttnParams p{};
   p.qkv = qkv; p.out = out; p.ld_qkv = 3LL * C; p.ld_out = C; p.C = C; p.heads = heads; p.ntok = window * window;
@@ -529,6 +532,7 @@ extern "C" int mvlt_window_attention(const void* qkv, void* out, int dtype, cons
 extern "C" int mvlt_joint_attention(const void* qkv, void* out, int dtype, const float* kmask, int B, int S, int heads,
                                     int head_dim, int seq2seq, int obj_end, float scale, cudaStream_t stream) {
   if (!qkv || !out || !kmask || B <= 0 || S <= 0 || heads <= 0) return MVLT_ERR_INVALID;
+  { const int rc0 = mvlt_attn_init(); if (rc0 != MVLT_OK) return rc0; }
   if (head_dim != 64) return MVLT_ERR_UNSUPPORTED;
   const int C = heads * head_dim;
   AttnParams p{};

@@ -31,6 +31,18 @@ namespace mvlt {
 
 typedef __nv_bfloat16 bf16;
 
+// Function attributes (opt-in shared memory sizes, carve-outs) are per DEVICE: true the first time the calling thread's
+// current device is seen for this `mask` (one mask per attribute group), so a process that drives several GPUs sets them
+// on each.  Not synchronised: the reference's callers are single-threaded.
+static inline bool first_use_on_device(unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 __device__ __forceinline__ void pdl_grid_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

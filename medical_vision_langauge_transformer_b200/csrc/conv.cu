@@ -364,14 +364,13 @@ extern "C" int mvlt_resnet_stem_tc(const float* img, const void* w, const float*
   const int Hp = (Ho + 2 - 3) / 2 + 1, Wp = (Wo + 2 - 3) / 2 + 1;      // maxpool: k 3, stride 2, pad 1
   const long long tiles = (long long)B * ((Hp + SP_ROWS - 1) / SP_ROWS) * ((Wp + SP_COLS - 1) / SP_COLS);
   if (tiles > 0x7fffffffLL) return MVLT_ERR_UNSUPPORTED;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devices = 0;
+  if (first_use_on_device(attr_devices)) {
     cudaError_t e = cudaFuncSetAttribute(resnet_stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
     if (e != cudaSuccess) return (int)e;
     // two CTAs per SM
     e = cudaFuncSetAttribute(resnet_stem_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

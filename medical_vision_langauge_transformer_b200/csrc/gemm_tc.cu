@@ -542,14 +542,19 @@ static Variant pick_variant(int act, bool out_bf16, int res, bool deep) {
 static PFN_cuTensorMapEncodeIm2col_v12000 g_encode_im2col = nullptr;
 
 static int gemm_tc_init() {
-  if (g_encode) return MVLT_OK;
-  void* fn = nullptr;
-  void* fn2 = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
-  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return MVLT_ERR_DRIVER;
-  e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn2, cudaEnableDefault, &q);
-  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn2) return MVLT_ERR_DRIVER;
+  static unsigned long long devices = 0;
+  if (!first_use_on_device(devices)) return MVLT_OK;
+  if (!g_encode) {
+    void* fn = nullptr;
+    void* fn2 = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return MVLT_ERR_DRIVER;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn2, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn2) return MVLT_ERR_DRIVER;
+    g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn2);
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
   for (int act = 0; act < 5; ++act)
     for (int o = 0; o < 2; ++o)
       for (int r = 0; r < 3; ++r)
@@ -557,14 +562,12 @@ static int gemm_tc_init() {
           if (d && (!r || act != 0 || o)) continue;
           const Variant v = pick_variant(act, o != 0, r, d != 0);
           if (!v.kernel) continue;
-          e = cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem);
+          cudaError_t e = cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem);
           if (e != cudaSuccess) return (int)e;
         }
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn2);
-  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   return MVLT_OK;
 }
 

@@ -374,11 +374,10 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_consta
 template <int C>
 static int launch_swin_mlp(const MlpParams& p, const void* w1, const void* w2, cudaStream_t stream) {
   using P = MlpPlan<C>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devices = 0;
+  if (first_use_on_device(attr_devices)) {
     cudaError_t e = cudaFuncSetAttribute(swin_mlp_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   CUtensorMap t1, t2;
   int rc;
@@ -585,11 +584,10 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
 template <int C, int ACT>
 static int launch_ln_linear(const LnGemmParams& p, const void* w, void* out, long long ldc, cudaStream_t stream) {
   using P = LnGemmPlan<C>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devices = 0;
+  if (first_use_on_device(attr_devices)) {
     cudaError_t e = cudaFuncSetAttribute(ln_linear_kernel<C, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   CUtensorMap tw, to;
   int rc;
