@@ -118,9 +118,18 @@ int mvlt_patch_embed_ln(const float* img, const float* weight, const float* bias
  * fp32-accurate (~1e-6 relative).  The bf16-mode stem: 5x faster than the FMA-bound kernel above. */
 int mvlt_patch_embed_ln_tc(const float* img, const float* weight, const float* bias, const float* gamma,
                            const float* beta, float* out, int B, int img_size, int patch, int embed_dim, float eps,
-                           const float* gamma2, const float* beta2, float eps2, void* out2_bf16, mvlt_stream_t stream);
+                           const float* gamma2, const float* beta2, float eps2, void* out2_bf16, int out2_window,
+                           mvlt_stream_t stream);
 /* out2_bf16 (or NULL): additionally LayerNorm(out; gamma2, beta2, eps2) rounded to bf16 [B*3136, 96] — norm1 of the first
- * Swin block (vfe.py:356) computed on the rows while they are still in registers. */
+ * Swin block (vfe.py:356) computed on the rows while they are still in registers.  out2_window > 0: its rows are written
+ * WINDOW-MAJOR (window_partition of vfe.py:144-156 with that window size, no shift) for mvlt_window_attention_tc. */
+
+/* LayerNorm(x) -> bf16 [B*H*W, C] with the OUTPUT ROWS in window-major order of the image rolled by -shift: row
+ * (b*nW + w)*window^2 + i = token i of window w — norm1 of a Swin block (vfe.py:356) fused with torch.roll (vfe.py:361) and
+ * window_partition (vfe.py:144-156, :363-364).  The qkv GEMM keeps the row order, so the tcgen05 window-attention kernel
+ * below fetches each window as one contiguous TMA box.  x fp32 [B*H*W, C] (row stride ld_in) in natural token order. */
+int mvlt_layernorm_rows_winmajor(const float* in, long long ld_in, void* out_bf16, const float* gamma, const float* beta, int B,
+                                 int H, int W, int C, int window, int shift, float eps, mvlt_stream_t stream);
 
 /* PatchMerging gather + LayerNorm(4C): x fp32 [B,H,W,C] -> out [B*H/2*W/2, 4C] in quad order (0,0),(1,0),(0,1),(1,1).
  * vfe.py:433-442 (the Linear(4C,2C) that follows is mvlt_gemm_*). */
@@ -135,6 +144,15 @@ int mvlt_patch_merge_ln(const float* x, void* out, int out_dtype, const float* g
  * key columns 49..55 = -1e30), 16-byte aligned — built once per block by the host (ops.window_bias_fragments). */
 int mvlt_window_attention(const void* qkv, void* out, int dtype, const float* relbias, int B, int H, int W, int C,
                           int heads, int window, int shift, float scale, mvlt_stream_t stream);
+
+/* The same attention on tcgen05 / TMEM / TMA (bf16): qkv [B*nW*49, 3C] with rows WINDOW-MAJOR for this block's shift (as
+ * written by mvlt_layernorm_rows_winmajor + the qkv GEMM), out [B*H*W, C] in NATURAL token order (window_reverse + the
+ * reverse roll of vfe.py:159-173, :373-381 are the output scatter).  Two windows per 128-lane accumulator tile, S = Q.K^T
+ * and O = P.V as tcgen05.mma with S, P and O in tensor memory, one score row per thread.  bias_table: fp32
+ * [n_cls][heads][49][52] = (relative-position bias + the -100 shift mask of vfe.py:318-344) * log2(e), n_cls = 4 window
+ * classes when shift > 0 else 1 (ops.window_bias_table), 16-byte aligned.  window must be 7, C == heads * 32. */
+int mvlt_window_attention_tc(const void* qkv, void* out, const float* bias_table, int B, int H, int W, int C, int heads,
+                             int window, int shift, float scale, mvlt_stream_t stream);
 
 /* Joint embedding assembly + additive key mask: model.py:110-160, :162-183.
  * feat [n_feat, n_obj, D]; img_index int32 [B] (row of feat per sample) or NULL for identity; ids int64 [B,L];
@@ -158,6 +176,13 @@ int mvlt_vit_embed(const float* patches, const float* cls, const float* pos, flo
  * features); the same kernel is the nn.MultiheadAttention of the ViT encoder blocks (kmask = 0). */
 int mvlt_joint_attention(const void* qkv, void* out, int dtype, const float* kmask, int B, int S, int heads,
                          int head_dim, int seq2seq, int obj_end, float scale, mvlt_stream_t stream);
+
+/* The same attention on tcgen05 / TMEM / TMA (bf16, head_dim 64): a tile is 128 consecutive rows of qkv for one head; the
+ * samples it touches are multiplied under the MMA's disable-output-lane mask, so every accumulator lane is a real row.
+ * S in [64, 96] or [128, 144] (the MVLT joint sequences 74 / 81 / 131); other lengths return MVLT_ERR_UNSUPPORTED and the
+ * caller uses mvlt_joint_attention. */
+int mvlt_joint_attention_tc(const void* qkv, void* out, const float* kmask, int B, int S, int heads, int head_dim, int seq2seq,
+                            int obj_end, float scale, mvlt_stream_t stream);
 
 /* out[r, n] = x[r,:] . w[n,:] + bias[n], N <= 16 (fp32 weights/outputs).  model.py:435, :363. */
 int mvlt_linear_small(const void* x, int x_dtype, long long ldx, const float* w, const float* bias, float* out,

@@ -28,7 +28,10 @@ PROTOTYPES = {
     "mvlt_gemm_f32_simt": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
     "mvlt_layernorm_rows": [_vp, _i, _ll, _vp, _i, _ll, _vp, _vp, _ll, _i, _f, _i, _vp, _ll, _vp],
     "mvlt_patch_embed_ln": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
-    "mvlt_patch_embed_ln_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _f, _vp, _vp],
+    "mvlt_patch_embed_ln_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _f, _vp, _i, _vp],
+    "mvlt_layernorm_rows_winmajor": [_vp, _ll, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "mvlt_window_attention_tc": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "mvlt_joint_attention_tc": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp],
     "mvlt_patch_merge_ln": [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "mvlt_window_attention": [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
     "mvlt_joint_embed": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],

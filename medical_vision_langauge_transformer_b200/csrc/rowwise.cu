@@ -10,6 +10,25 @@
 
 namespace mvlt {
 
+// Optional output-row permutation of the LayerNorm in front of a Swin qkv GEMM: natural token row (b, h, x) -> WINDOW-MAJOR
+// row (b*nW + w)*ws*ws + i of the image rolled by -shift (vfe.py:361 torch.roll + :144-156 window_partition), so that the
+// tcgen05 window-attention kernel fetches a window as one contiguous TMA box.  H == 0: identity.
+struct WinMap {
+  int H, W, ws, shift;
+  __device__ __forceinline__ long long operator()(long long row) const {
+    if (H == 0) return row;
+    const int hw = H * W;
+    const long long b = row / hw;
+    const int rem = (int)(row - b * hw);
+    int h = rem / W, x = rem - h * W;
+    h -= shift; if (h < 0) h += H;        // the token at (h, x) sits at (h - shift, x - shift) of the rolled image
+    x -= shift; if (x < 0) x += W;
+    const int nWw = W / ws;
+    const int w = (h / ws) * nWw + x / ws, i = (h % ws) * ws + x % ws;
+    return (b * (long long)((H / ws) * nWw) + w) * (ws * ws) + i;
+  }
+};
+
 // One warp normalises one row of C elements (C % 4 == 0, C <= 128*NCH).  `src(c)` returns the 4 elements
 // starting at column c.  Two-pass statistics from registers (mean, then centred sum of squares).
 template <int NCH, typename TO, typename SrcFn>
@@ -61,12 +80,12 @@ template <int NCH, typename TI, typename TO>
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const TI* __restrict__ in, long long ld_in, TO* __restrict__ out, long long ld_out,
                       const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, int C, float eps,
-                      int gelu, bf16* __restrict__ out_copy, long long ld_copy) {
+                      int gelu, bf16* __restrict__ out_copy, long long ld_copy, const WinMap wm) {
   pdl_grid_sync();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const TI* src = in + row * ld_in;
-  ln_row_core<NCH>([&](int c) { return load4(src + c); }, out + row * ld_out, gamma, beta, C, eps, gelu != 0,
+  ln_row_core<NCH>([&](int c) { return load4(src + c); }, out + wm(row) * ld_out, gamma, beta, C, eps, gelu != 0,
                    threadIdx.x & 31, out_copy ? out_copy + row * ld_copy : nullptr);
 }
 
@@ -76,7 +95,7 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
 layernorm_rows_small_kernel(const TI* __restrict__ in, long long ld_in, TO* __restrict__ out, long long ld_out,
                             const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, int C, float eps,
-                            int gelu, bf16* __restrict__ out_copy, long long ld_copy) {
+                            int gelu, bf16* __restrict__ out_copy, long long ld_copy, const WinMap wm) {
   pdl_grid_sync();
   const int lane = threadIdx.x & 31, sub = lane & 7;
   const long long row = (long long)blockIdx.x * 32 + (threadIdx.x >> 5) * 4 + (lane >> 3);
@@ -103,6 +122,7 @@ layernorm_rows_small_kernel(const TI* __restrict__ in, long long ld_in, TO* __re
   q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
   const float rstd = 1.0f / sqrtf(q / (float)C + eps);
   if (!live) return;
+  const long long orow = wm(row);
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     if (i < nq) {
@@ -117,7 +137,7 @@ layernorm_rows_small_kernel(const TI* __restrict__ in, long long ld_in, TO* __re
       if (gelu) {
         o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w);
       }
-      store4(out + row * ld_out + c, o);
+      store4(out + orow * ld_out + c, o);
       if (out_copy) store4(out_copy + row * ld_copy + c, o);
     }
 }
@@ -231,7 +251,7 @@ __global__ void __launch_bounds__(PT_WARPS * 32, 3)
 patch_embed_ln_tc_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
                          const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
                          float eps, int n_groups, const float* __restrict__ gamma2, const float* __restrict__ beta2,
-                         float eps2, bf16* __restrict__ out2) {
+                         float eps2, bf16* __restrict__ out2, int out2_window) {
   __shared__ __align__(16) bf16 w_hi[PE_C * PT_LDW];
   __shared__ __align__(16) bf16 w_lo[PE_C * PT_LDW];
   __shared__ __align__(16) float4 s_gb[PE_C / 2];   // (gamma[c], gamma[c+1], beta[c], beta[c+1]) for even c
@@ -260,11 +280,17 @@ patch_embed_ln_tc_kernel(const float* __restrict__ img, const float* __restrict_
     // rows g and g+8 of the 16-patch tile
     const float* src[2];
     float* dst[2];
+    long long row2[2];   // row of the second output: natural, or window-major (window = out2_window, no shift) for the tcgen05 attention
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int P = grp * 16 + g + 8 * r;
       const int b = P / (PE_P * PE_P), rem = P - b * (PE_P * PE_P);
       const int py = rem / PE_P, px = rem - py * PE_P;
+      row2[r] = P;
+      if (out2_window > 0) {
+        const int ws = out2_window, nWw = PE_P / ws;
+        row2[r] = ((long long)b * (nWw * nWw) + (py / ws) * nWw + px / ws) * (ws * ws) + (py % ws) * ws + px % ws;
+      }
       src[r] = img + ((long long)b * 3 * PE_IMG + 4 * py + (t >> 1)) * PE_IMG + 4 * px + 2 * (t & 1);
       dst[r] = out + (long long)P * PE_C + 2 * t;
     }
@@ -342,7 +368,7 @@ patch_embed_ln_tc_kernel(const float* __restrict__ img, const float* __restrict_
       p0 += __shfl_xor_sync(0xffffffffu, p0, 1); p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
       p1 += __shfl_xor_sync(0xffffffffu, p1, 1); p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
       const float z0 = 1.0f / sqrtf(p0 * (1.0f / PE_C) + eps2), z1 = 1.0f / sqrtf(p1 * (1.0f / PE_C) + eps2);
-      bf16* d0 = out2 + (dst[0] - out), * d1 = out2 + (dst[1] - out);
+      bf16* d0 = out2 + row2[0] * PE_C + 2 * t, * d1 = out2 + row2[1] * PE_C + 2 * t;
 #pragma unroll
       for (int nt = 0; nt < 12; ++nt) {
         const float4 gb = s_gb2[nt * 4 + t];
@@ -414,16 +440,17 @@ joint_embed_kernel(const TF* __restrict__ feat, const int* __restrict__ img_inde
 
 template <typename TI, typename TO>
 static int launch_ln(const void* in, long long ld_in, void* out, long long ld_out, const float* gamma, const float* beta,
-                     long long rows, int C, float eps, int gelu, void* out_copy, long long ld_copy, cudaStream_t st) {
+                     long long rows, int C, float eps, int gelu, void* out_copy, long long ld_copy, cudaStream_t st,
+                     WinMap wm = WinMap{0, 0, 1, 0}) {
   if (C <= 128 && C % 32 == 0) {
     launch_k(layernorm_rows_small_kernel<TI, TO>, dim3((unsigned)((rows + 31) / 32)), dim3(256), 0, st, (const TI*)in, ld_in,
-             (TO*)out, ld_out, gamma, beta, rows, C, eps, gelu, (bf16*)out_copy, ld_copy);
+             (TO*)out, ld_out, gamma, beta, rows, C, eps, gelu, (bf16*)out_copy, ld_copy, wm);
     return MVLT_OK;
   }
   const unsigned grid = (unsigned)((rows + 7) / 8);
 #define LN_CASE(NCH)                                                                                              \
   launch_k(layernorm_rows_kernel<NCH, TI, TO>, dim3(grid), dim3(256), 0, st, (const TI*)in, ld_in, (TO*)out, ld_out, gamma, beta, \
-                                                           rows, C, eps, gelu, (bf16*)out_copy, ld_copy)
+                                                           rows, C, eps, gelu, (bf16*)out_copy, ld_copy, wm)
   if (C <= 128) LN_CASE(1);
   else if (C <= 256) LN_CASE(2);
   else if (C <= 384) LN_CASE(3);
@@ -473,6 +500,19 @@ extern "C" int mvlt_layernorm_rows(const void* in, int in_dtype, long long ld_in
   return MVLT_OK;
 }
 
+// LayerNorm(x) -> bf16 with the output rows in WINDOW-MAJOR order of the image rolled by -shift (see WinMap): norm1 of a Swin
+// block (vfe.py:356) fused with torch.roll + window_partition (vfe.py:361-367).  x: fp32 [B*H*W, C] natural token order.
+extern "C" int mvlt_layernorm_rows_winmajor(const float* in, long long ld_in, void* out_bf16, const float* gamma, const float* beta,
+                                            int B, int H, int W, int C, int window, int shift, float eps, cudaStream_t stream) {
+  if (!in || !out_bf16 || !gamma || !beta || B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 4 || ld_in % 4) return MVLT_ERR_INVALID;
+  if (window <= 0 || H % window || W % window || shift < 0 || shift >= window) return MVLT_ERR_INVALID;
+  const int rc = launch_ln<float, bf16>(in, ld_in, out_bf16, C, gamma, beta, (long long)B * H * W, C, eps, 0, nullptr, 0, stream,
+                                        WinMap{H, W, window, shift});
+  if (rc != MVLT_OK) return rc;
+  MVLT_LAUNCH_CHECK();
+  return MVLT_OK;
+}
+
 extern "C" int mvlt_patch_embed_ln(const float* img, const float* weight, const float* bias, const float* gamma,
                                    const float* beta, float* out, int B, int img_size, int patch, int embed_dim,
                                    float eps, cudaStream_t stream) {
@@ -487,10 +527,11 @@ extern "C" int mvlt_patch_embed_ln(const float* img, const float* weight, const 
 extern "C" int mvlt_patch_embed_ln_tc(const float* img, const float* weight, const float* bias, const float* gamma,
                                       const float* beta, float* out, int B, int img_size, int patch, int embed_dim,
                                       float eps, const float* gamma2, const float* beta2, float eps2, void* out2_bf16,
-                                      cudaStream_t stream) {
+                                      int out2_window, cudaStream_t stream) {
   if (!img || !weight || !bias || !gamma || !beta || !out || B <= 0) return MVLT_ERR_INVALID;
   if (out2_bf16 && (!gamma2 || !beta2 || ((uintptr_t)out2_bf16 & 3))) return MVLT_ERR_INVALID;
   if (img_size != PE_IMG || patch != 4 || embed_dim != PE_C) return MVLT_ERR_UNSUPPORTED;
+  if (out2_window < 0 || (out2_window > 0 && PE_P % out2_window != 0)) return MVLT_ERR_INVALID;
   if (((uintptr_t)img & 7) || ((uintptr_t)out & 7)) return MVLT_ERR_INVALID;
   const int n_groups = B * (PE_P * PE_P / 16);
   int dev = 0, sms = 148;
@@ -498,7 +539,7 @@ extern "C" int mvlt_patch_embed_ln_tc(const float* img, const float* weight, con
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ctas = (n_groups + PT_WARPS - 1) / PT_WARPS;
   launch_k(patch_embed_ln_tc_kernel, dim3(ctas < 3 * sms ? ctas : 3 * sms), dim3(PT_WARPS * 32), 0, stream, img, weight, bias,
-           gamma, beta, out, eps, n_groups, gamma2, beta2, eps2, reinterpret_cast<bf16*>(out2_bf16));
+           gamma, beta, out, eps, n_groups, gamma2, beta2, eps2, reinterpret_cast<bf16*>(out2_bf16), out2_window);
   MVLT_LAUNCH_CHECK();
   return MVLT_OK;
 }

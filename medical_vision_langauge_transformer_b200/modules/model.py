@@ -173,6 +173,9 @@ class MVLBert(_PackedMixin, nn.Module):
         The hidden state / residual stays fp32 in both precisions; in bf16 mode every LayerNorm also emits the rows
         rounded to bf16 as the A operand of the next tcgen05 GEMM (the residual path never sees bf16 rounding)."""
         cfg = self.config
+        if self.training and (cfg.hidden_dropout_prob > 0 or cfg.attention_probs_dropout_prob > 0):
+            raise NotImplementedError("train mode (Dropout, HF modeling_bert.py:296,:353) is outside the accelerated forward path; "
+                                      "call model.eval() — this package implements the eval-mode forward only")
         pk = self.packed()
         bf = self.precision == "bf16"
         image_feature = image_feature.float().contiguous()
@@ -302,10 +305,57 @@ class MVLBertPretrainedModel(PreTrainedModel):
     config_class = MVLBertConfig
     _keys_to_ignore_on_load_missing = [r"position_ids"]
 
+    _constructing = False
+
+    def __init__(self, config, *args, **kwargs):
+        # Fresh construction keeps PyTorch-default initialisation exactly as in the reference, where `init_weights()` is never
+        # called (model.py:365): `_init_weights` is inert until `post_init()` (end of every task `__init__`) has run.
+        self._constructing = True
+        super().__init__(config, *args, **kwargs)
+
+    def _finish_init(self):
+        self.post_init()
+        self._constructing = False
+
     def _init_weights(self, module):
-        # Never invoked by the reference (init_weights() is commented out, model.py:365): PyTorch defaults stand.
-        # Kept as a no-op so that HF's post_init/from_pretrained machinery does not re-initialise anything.
-        return
+        """model.py:280-294, applied by `from_pretrained` to the tensors a checkpoint does NOT provide (HF builds the model on a
+        meta device, so whatever is not loaded has no values): Linear / Embedding ~ N(0, initializer_range), LayerNorm = (1, 0).
+        Beyond the reference: the input-independent buffers and the non-Linear parameters get their constructor values back.
+        Every initialiser below skips tensors already loaded (`_is_hf_initialized`)."""
+        if self._constructing:
+            return
+        from transformers import initialization as init
+        from .visual_feature_extractor import SwinTransformerBlock, WindowAttention
+        std = self.config.initializer_range
+        if isinstance(module, nn.Linear):
+            init.normal_(module.weight, mean=0.0, std=std)
+            if module.bias is not None:
+                init.zeros_(module.bias)
+        elif isinstance(module, nn.Embedding):
+            init.normal_(module.weight, mean=0.0, std=std)
+        elif isinstance(module, nn.LayerNorm):
+            init.zeros_(module.bias)
+            init.ones_(module.weight)
+        elif isinstance(module, nn.Conv2d):
+            init.kaiming_uniform_(module.weight, a=5 ** 0.5)
+            if module.bias is not None:
+                init.zeros_(module.bias)
+        elif isinstance(module, nn.BatchNorm2d):
+            init.ones_(module.weight); init.zeros_(module.bias)
+            init.zeros_(module.running_mean); init.ones_(module.running_var); init.zeros_(module.num_batches_tracked)
+        elif isinstance(module, WindowAttention):
+            init.trunc_normal_(module.relative_position_bias_table, std=0.02)
+            init.copy_(module.relative_position_index, module.build_relative_position_index())
+        elif isinstance(module, SwinTransformerBlock):
+            if module.attn_mask is not None:
+                init.copy_(module.attn_mask, module.build_attn_mask())
+        elif isinstance(module, MVLBert):
+            init.copy_(module.position_ids, torch.arange(module.position_ids.shape[-1]).expand((1, -1)))
+        elif isinstance(module, _LMPredictionHead):
+            init.zeros_(module.bias)
+        else:
+            for prm in module.parameters(recurse=False):      # class tokens / position embeddings of the ViT variant
+                init.normal_(prm, mean=0.0, std=std)
 
     @property
     def precision(self):
@@ -337,6 +387,7 @@ class MVLBertForVQA(_PackedMixin, MVLBertPretrainedModel):
         self.final_mlp = nn.Sequential(nn.Dropout(config.hidden_dropout_prob, inplace=False),
                                        nn.Linear(config.hidden_size, config.result_num))
         self.softmax = nn.Softmax(dim=-1)
+        self._finish_init()
 
     def _pack_params(self):
         return self.final_mlp.parameters()
@@ -364,6 +415,7 @@ class MVLBertForRetrieval(_PackedMixin, MVLBertPretrainedModel):
         self.final_mlp = nn.Sequential(_DenseLN(config, config.hidden_size), nn.Linear(config.hidden_size, 2))
         self.softmax = nn.Softmax(dim=1)
         self.sigmoid = nn.Sigmoid()
+        self._finish_init()
 
     def _pack_params(self):
         return self.final_mlp.parameters()
@@ -402,6 +454,7 @@ class MVLBertForPretraining(_PackedMixin, MVLBertPretrainedModel):
         self.MLM_head_seq2seq = _OnlyMLMHead(config)
         self.MLM_head_bidir = _OnlyMLMHead(config)
         self.ITM_mlp = nn.Linear(config.hidden_size, 2)
+        self._finish_init()
 
     def _pack_params(self):
         return [*self.MLM_head_seq2seq.parameters(), *self.MLM_head_bidir.parameters(), *self.ITM_mlp.parameters()]
@@ -425,7 +478,7 @@ class MVLBertForPretraining(_PackedMixin, MVLBertPretrainedModel):
         adt = act_dtype(self.precision)
         n_obj, L, D = feat.shape[1], caption_masked.shape[1], hidden.shape[1]
         pk = self.packed()
-        mlm_loss = torch.zeros((1, 1))
+        mlm_loss = torch.zeros((1, 1), device=hidden.device)     # model.py:405 (a CUDA tensor there as well once .cuda()'d)
         if cfg.MLM_task:
             w = pk["seq2seq" if seq2seq else "bidir"]
             src = shadow if shadow is not None else hidden                                # GEMM A operand dtype
@@ -459,6 +512,7 @@ class MVLBertForImageCaption(_PackedMixin, MVLBertPretrainedModel):
         self.conv = Conv_layer(config)
         self.tokenizer = tokenizer
         self.MLM_head_seq2seq = _OnlyMLMHead(config)
+        self._finish_init()
 
     def _pack_params(self):
         return self.MLM_head_seq2seq.parameters()

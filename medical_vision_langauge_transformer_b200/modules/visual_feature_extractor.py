@@ -59,15 +59,20 @@ class WindowAttention(nn.Module):
         self.scale = qk_scale or (dim // num_heads) ** -0.5
         wh, ww = self.window_size
         self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * wh - 1) * (2 * ww - 1), num_heads))
-        ys, xs = torch.meshgrid(torch.arange(wh), torch.arange(ww), indexing="ij")
-        coords = torch.stack([ys.flatten(), xs.flatten()])
-        d = coords[:, :, None] - coords[:, None, :]
-        self.register_buffer("relative_position_index", (d[0] + wh - 1) * (2 * ww - 1) + (d[1] + ww - 1))
+        self.register_buffer("relative_position_index", self.build_relative_position_index())
         self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
         self.attn_drop = nn.Dropout(attn_drop)
         self.proj = nn.Linear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
         _trunc_normal_(self.relative_position_bias_table)
+
+    def build_relative_position_index(self) -> torch.Tensor:
+        """vfe.py:203-214 (input independent; also used to restore the buffer when a checkpoint lacks it)."""
+        wh, ww = self.window_size
+        ys, xs = torch.meshgrid(torch.arange(wh), torch.arange(ww), indexing="ij")
+        coords = torch.stack([ys.flatten(), xs.flatten()])
+        d = coords[:, :, None] - coords[:, None, :]
+        return (d[0] + wh - 1) * (2 * ww - 1) + (d[1] + ww - 1)
 
     def gathered_bias(self) -> torch.Tensor:
         """[heads, 64, 64] fp32, zero padded: table[index] permuted as vfe.py:236-238 (input independent)."""
@@ -97,19 +102,22 @@ class SwinTransformerBlock(nn.Module):
         self.drop_path = nn.Identity()
         self.norm2 = norm_layer(dim)
         self.mlp = Mlp(dim, int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
-        mask = None
-        if self.shift_size > 0:
-            H, W = self.input_resolution
-            ws, sh = self.window_size, self.shift_size
-            region = torch.zeros(H, W)
-            bounds = ((0, H - ws), (H - ws, H - sh), (H - sh, H))
-            for a, (h0, h1) in enumerate(bounds):
-                for b, (w0, w1) in enumerate(((0, W - ws), (W - ws, W - sh), (W - sh, W))):
-                    region[h0:h1, w0:w1] = 3 * a + b
-            win = region.view(H // ws, ws, W // ws, ws).permute(0, 2, 1, 3).reshape(-1, ws * ws)
-            diff = win[:, None, :] - win[:, :, None]
-            mask = torch.where(diff != 0, torch.full_like(diff, -100.0), torch.zeros_like(diff))
-        self.register_buffer("attn_mask", mask)
+        self.register_buffer("attn_mask", self.build_attn_mask())
+
+    def build_attn_mask(self):
+        """vfe.py:318-348: -100 between tokens of different regions of the rolled image (None for unshifted blocks)."""
+        if self.shift_size == 0:
+            return None
+        H, W = self.input_resolution
+        ws, sh = self.window_size, self.shift_size
+        region = torch.zeros(H, W)
+        bounds = ((0, H - ws), (H - ws, H - sh), (H - sh, H))
+        for a, (h0, h1) in enumerate(bounds):
+            for b, (w0, w1) in enumerate(((0, W - ws), (W - ws, W - sh), (W - sh, W))):
+                region[h0:h1, w0:w1] = 3 * a + b
+        win = region.view(H // ws, ws, W // ws, ws).permute(0, 2, 1, 3).reshape(-1, ws * ws)
+        diff = win[:, None, :] - win[:, :, None]
+        return torch.where(diff != 0, torch.full_like(diff, -100.0), torch.zeros_like(diff))
 
 
 class PatchMerging(nn.Module):
@@ -170,7 +178,8 @@ class SwinTransformer(nn.Module):
         self.patch_embed = PatchEmbed(img_size, patch_size, in_chans, embed_dim, norm_layer if patch_norm else None)
         self.patches_resolution = self.patch_embed.patches_resolution
         self.pos_drop = nn.Dropout(p=drop_rate)
-        dpr = torch.linspace(0, drop_path_rate, sum(depths)).tolist()
+        n_blocks = sum(depths)   # torch.linspace(0, rate, n) of vfe.py:633 in plain Python (HF builds models under a meta device)
+        dpr = [drop_path_rate * i / max(n_blocks - 1, 1) for i in range(n_blocks)]
         res = self.patches_resolution
         self.layers = nn.ModuleList([
             BasicLayer(int(embed_dim * 2 ** i), (res[0] // 2 ** i, res[1] // 2 ** i), depths[i], num_heads[i], window_size,
@@ -219,7 +228,9 @@ class SwinTransformer(nn.Module):
                         fc2_w=wcast(blk.mlp.fc2.weight), fc2_b=f32(blk.mlp.fc2.bias),
                         relbias=(ops.window_bias_fragments(blk.attn.gathered_bias(), blk.shift_size, blk.attn.scale,
                                                            blk.window_size)
-                                 if self.precision == "bf16" else blk.attn.gathered_bias())))
+                                 if self.precision == "bf16" else blk.attn.gathered_bias()),
+                        bias_tc=(ops.window_bias_table(blk.attn.gathered_bias(), blk.shift_size, blk.window_size)
+                                 if self.precision == "bf16" else None)))
                 if layer.downsample is not None:
                     pk["merge"].append(dict(nw=f32(layer.downsample.norm.weight), nb=f32(layer.downsample.norm.bias),
                                             red_w=wcast(layer.downsample.reduction.weight)))
@@ -229,6 +240,9 @@ class SwinTransformer(nn.Module):
     # ---------------------------------------------------------------- forward
     def forward_features(self, x, final_gelu: bool = False, out_dtype=None):
         pe = self.patch_embed
+        if self.training and (any(getattr(b, "drop_path_rate", 0.0) > 0 for l in self.layers for b in l.blocks) or self.pos_drop.p > 0):
+            raise NotImplementedError("train mode (DropPath / Dropout, vfe.py:313,:633) is outside the accelerated forward path; "
+                                      "call model.eval() — this package implements the eval-mode forward only")
         B, C_in, H_img, W_img = x.shape
         assert H_img == pe.img_size[0] and W_img == pe.img_size[1], \
             f"Input image size ({H_img}*{W_img}) doesn't match model ({pe.img_size[0]}*{pe.img_size[1]})."
@@ -238,10 +252,15 @@ class SwinTransformer(nn.Module):
         adt = act_dtype(self.precision)
         x = x.contiguous().float()
         a_first = None
+        # bf16 mode: window attention on tcgen05 (MVLT_ATTN=tc, default) reads qkv rows WINDOW-MAJOR: norm1 writes its bf16
+        # output in that order (roll + window_partition cost nothing), the qkv GEMM keeps it, the attention kernel scatters
+        # its output back to natural order.  MVLT_ATTN=warp: the mma.sync kernel of round 1 on natural-order rows.
+        attn_tc = self.precision == "bf16" and ops.attention_impl() == "tc"
         if self.precision == "bf16":   # tensor-core stem; norm1 of block 0 comes out of the same kernel
             b0 = self.layers[0].blocks[0]
             X, a_first = ops.patch_embed_ln(x, pk["pe_w"], pk["pe_b"], pe.norm.weight, pe.norm.bias, pe.norm.eps,
-                                            tensor_cores=True, next_norm=(pk["blocks"][0]["n1w"], pk["blocks"][0]["n1b"], b0.norm1.eps))
+                                            tensor_cores=True, next_norm=(pk["blocks"][0]["n1w"], pk["blocks"][0]["n1b"], b0.norm1.eps),
+                                            next_norm_window=b0.window_size if (attn_tc and b0.window_size == 7) else 0)
         else:
             X = ops.patch_embed_ln(x, pk["pe_w"], pk["pe_b"], pe.norm.weight, pe.norm.bias, pe.norm.eps)
         # LN2 + fc1 + GELU + fc2 + residual as ONE tcgen05 kernel (csrc/swin_mlp.cu) for the stage widths listed in
@@ -268,16 +287,24 @@ class SwinTransformer(nn.Module):
                 w = pk["blocks"][bi]
                 bi += 1
                 ln_lin = C in ln_lin_widths and C in ops.FUSED_LN_LINEAR_WIDTHS
+                win_tc = attn_tc and blk.window_size == 7 and H % 7 == 0 and W % 7 == 0
                 if a_first is not None:
                     a, a_first = a_first, None
+                    qkv = ops.linear(a, w["qkv_w"], w["qkv_b"])
+                elif win_tc:
+                    a = ops.layernorm_winmajor(X, w["n1w"], w["n1b"], blk.norm1.eps, B, H, W, blk.window_size, blk.shift_size)
                     qkv = ops.linear(a, w["qkv_w"], w["qkv_b"])
                 elif ln_lin:
                     qkv = ops.ln_linear(X, w["n1w"], w["n1b"], blk.norm1.eps, w["qkv_w"], w["qkv_b"])
                 else:
                     a = ops.layernorm(X, w["n1w"], w["n1b"], blk.norm1.eps, adt)
                     qkv = ops.linear(a, w["qkv_w"], w["qkv_b"])
-                o = ops.window_attention(qkv, w["relbias"], B, H, W, C, blk.num_heads, blk.window_size, blk.shift_size,
-                                         blk.attn.scale)
+                if win_tc:
+                    o = ops.window_attention_tc(qkv, w["bias_tc"], B, H, W, C, blk.num_heads, blk.window_size, blk.shift_size,
+                                                blk.attn.scale)
+                else:
+                    o = ops.window_attention(qkv, w["relbias"], B, H, W, C, blk.num_heads, blk.window_size, blk.shift_size,
+                                             blk.attn.scale)
                 ops.linear(o, w["proj_w"], w["proj_b"], residual=X, out=X)
                 if C in fused_widths and C in ops.FUSED_MLP_WIDTHS and w["fc1_w"].shape[0] == 4 * C:
                     ops.swin_mlp(X, w["n2w"], w["n2b"], blk.norm2.eps, w["fc1_w"], w["fc1_b"], w["fc2_w"], w["fc2_b"])
@@ -528,6 +555,16 @@ class _ViTMLP(nn.Sequential):
 
     def __init__(self, d, hidden):
         super().__init__(nn.Linear(d, hidden), nn.GELU(), nn.Dropout(0.0), nn.Linear(hidden, d), nn.Dropout(0.0))
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        # torchvision < 0.13 (the reference pins >= 0.12, README.md:5) stored the block as `linear_1` / `linear_2`;
+        # torchvision's own MLPBlock._load_from_state_dict performs the same rename
+        for old, new in (("linear_1", "0"), ("linear_2", "3")):
+            for kind in ("weight", "bias"):
+                k = f"{prefix}{old}.{kind}"
+                if k in state_dict:
+                    state_dict[f"{prefix}{new}.{kind}"] = state_dict.pop(k)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
 
 
 class _ViTEncoderBlock(nn.Module):

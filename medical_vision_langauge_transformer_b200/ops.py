@@ -31,6 +31,11 @@ def _ptr(t: Optional[torch.Tensor]):
 def _rows2d(t: torch.Tensor):
     """(rows, cols, ld) of a tensor viewed as a row-major matrix with unit inner stride."""
     assert t.is_cuda and t.dim() >= 2 and t.stride(-1) == 1, "expected a CUDA tensor with contiguous last dim"
+    if t.device.index != torch.cuda.current_device():
+        # the C ABI launches on the CURRENT device's stream and keys its per-device setup on it (unlike a torch op, which
+        # follows its tensors): refuse instead of launching on the wrong GPU with foreign pointers
+        raise RuntimeError(f"mvlt_b200 ops run on the current CUDA device ({torch.cuda.current_device()}), but got a tensor on "
+                           f"{t.device}; wrap the call in `with torch.cuda.device(tensor.device):`")
     if t.dim() == 2:
         return t.shape[0], t.shape[1], t.stride(0)
     assert t.is_contiguous()
@@ -205,10 +210,11 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 
 def patch_embed_ln(img: torch.Tensor, w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
-                   eps: float = 1e-5, tensor_cores: bool = False, next_norm=None):
+                   eps: float = 1e-5, tensor_cores: bool = False, next_norm=None, next_norm_window: int = 0):
     """Conv2d(3,96,k4,s4) + LayerNorm(96).  tensor_cores=True: the mma.sync kernel with bf16 hi/lo operand splitting
     (fp32-accurate, the bf16-mode stem); False: the fp32 CUDA-core kernel (parity mode).
-    next_norm=(gamma2, beta2, eps2) (tensor-core kernel only): also returns LayerNorm(out; gamma2, beta2) in bf16."""
+    next_norm=(gamma2, beta2, eps2) (tensor-core kernel only): also returns LayerNorm(out; gamma2, beta2) in bf16;
+    next_norm_window > 0 writes that second output window-major (see layernorm_winmajor)."""
     lib = _lib.ensure_init()
     B = img.shape[0]
     assert img.dtype == torch.float32 and img.is_contiguous() and w.is_contiguous()
@@ -223,7 +229,7 @@ def patch_embed_ln(img: torch.Tensor, w: torch.Tensor, b: torch.Tensor, gamma: t
             out2 = torch.empty((B * n_tok, E), device=img.device, dtype=torch.bfloat16)
         rc = lib.mvlt_patch_embed_ln_tc(img.data_ptr(), w.data_ptr(), b.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                         out.data_ptr(), B, img.shape[-1], P, E, float(eps), _ptr(g2), _ptr(b2), float(eps2),
-                                        _ptr(out2), _stream())
+                                        _ptr(out2), int(next_norm_window), _stream())
         _lib.check(rc, "mvlt_patch_embed_ln_tc")
         return (out, out2) if next_norm is not None else out
     assert next_norm is None
@@ -242,6 +248,81 @@ def patch_merge_ln(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, B: 
                                  float(eps), _stream())
     _lib.check(rc, "mvlt_patch_merge_ln")
     return out
+
+
+def layernorm_winmajor(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, B: int, H: int, W: int,
+                       window: int, shift: int) -> torch.Tensor:
+    """LayerNorm rows of the fp32 [B*H*W, C] token matrix -> bf16, written WINDOW-MAJOR for the image rolled by -shift:
+    row (b*nW + w)*window^2 + i (vfe.py:356 + the roll / window_partition of :361-364)."""
+    lib = _lib.ensure_init()
+    rows, C, ld = _rows2d(x)
+    assert x.dtype == torch.float32 and rows == B * H * W
+    out = torch.empty((rows, C), device=x.device, dtype=torch.bfloat16)
+    rc = lib.mvlt_layernorm_rows_winmajor(x.data_ptr(), ld, out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, H, W, C,
+                                          window, shift, float(eps), _stream())
+    _lib.check(rc, "mvlt_layernorm_rows_winmajor")
+    return out
+
+
+def window_major_index(B: int, H: int, W: int, window: int, shift: int, device=None) -> torch.Tensor:
+    """perm[natural token row] = window-major row (the map of layernorm_winmajor); host-side helper for tests / tools."""
+    r = torch.arange(B * H * W, device=device)
+    b, rem = r // (H * W), r % (H * W)
+    h, x = (rem // W - shift) % H, (rem % W - shift) % W
+    nWw = W // window
+    w, i = (h // window) * nWw + x // window, (h % window) * window + x % window
+    return (b * (H // window) * nWw + w) * window * window + i
+
+
+_LOG2E = 1.4426950408889634
+WIN_BIAS_LD = 52
+
+
+def window_bias_table(relbias: torch.Tensor, shift: int, window: int = 7) -> torch.Tensor:
+    """Input-independent table of the tcgen05 window-attention kernel: fp32 [n_cls, heads, 49, 52] =
+    (gathered relative-position bias [heads, 64, 64] (vfe.py:236-238) + the -100 shift mask (vfe.py:318-344)) * log2(e),
+    columns 49..51 zero.  Window classes as in window_bias_fragments: bit 1 = last window row, bit 0 = last window column."""
+    heads, n = relbias.shape[0], window * window
+    dev = relbias.device
+    i = torch.arange(n, device=dev)
+    r, c = i // window, i % window
+    n_cls = 4 if shift > 0 else 1
+    out = torch.zeros(n_cls, heads, n, WIN_BIAS_LD, device=dev, dtype=torch.float32)
+    for cls in range(n_cls):
+        rh = torch.where(r < window - shift, 1, 2) if cls & 2 else torch.zeros_like(r)
+        rw = torch.where(c < window - shift, 1, 2) if cls & 1 else torch.zeros_like(c)
+        reg = rh * 3 + rw
+        mask = torch.where(reg[:, None] != reg[None, :], -100.0, 0.0).to(torch.float32)
+        out[cls, :, :, :n] = (relbias[:, :n, :n].float() + mask[None]) * _LOG2E
+    return out.contiguous()
+
+
+def window_attention_tc(qkv: torch.Tensor, bias_table: torch.Tensor, B: int, H: int, W: int, C: int, heads: int, window: int,
+                        shift: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """tcgen05 window attention: bf16 qkv [B*H*W, 3C] with WINDOW-MAJOR rows -> bf16 out [B*H*W, C] in natural token order."""
+    lib = _lib.ensure_init()
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (B * H * W, 3 * C)
+    assert bias_table.dtype == torch.float32 and bias_table.is_contiguous()
+    assert bias_table.shape == (4 if shift > 0 else 1, heads, window * window, WIN_BIAS_LD), "takes window_bias_table()"
+    if out is None:
+        out = torch.empty((B * H * W, C), device=qkv.device, dtype=torch.bfloat16)
+    rc = lib.mvlt_window_attention_tc(qkv.data_ptr(), out.data_ptr(), bias_table.data_ptr(), B, H, W, C, heads, window, shift,
+                                      float(scale), _stream())
+    _lib.check(rc, "mvlt_window_attention_tc")
+    return out
+
+
+def attention_impl() -> str:
+    """'tc' (default): tcgen05 / TMEM / TMA attention kernels in bf16 mode; 'warp': the mma.sync kernels of round 1."""
+    import os
+    v = os.environ.get("MVLT_ATTN", "tc").strip().lower()
+    if v not in ("tc", "warp"):
+        raise ValueError(f"MVLT_ATTN={v!r}: expected 'tc' or 'warp'")
+    return v
+
+
+def joint_attention_tc_supported(S: int, head_dim: int) -> bool:
+    return head_dim == 64 and (64 <= S <= 96 or 128 <= S <= 144)
 
 
 _NEG_BIG = -1.0e30
@@ -335,13 +416,21 @@ def vit_embed(patches: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, B: in
 
 
 def joint_attention(qkv: torch.Tensor, kmask: torch.Tensor, B: int, S: int, heads: int, seq2seq: bool, obj_end: int,
-                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    out: Optional[torch.Tensor] = None, impl: Optional[str] = None) -> torch.Tensor:
+    """bf16: the tcgen05 kernel for the joint sequence lengths it covers (impl 'tc', default), else the mma.sync kernel."""
     lib = _lib.ensure_init()
     C = qkv.shape[1] // 3
     hd = C // heads
     assert qkv.is_contiguous() and qkv.shape[0] == B * S and kmask.shape == (B, S)
     if out is None:
         out = torch.empty((B * S, C), device=qkv.device, dtype=qkv.dtype)
+    if impl is None:
+        impl = attention_impl()
+    if qkv.dtype == torch.bfloat16 and impl == "tc" and joint_attention_tc_supported(S, hd):
+        rc = lib.mvlt_joint_attention_tc(qkv.data_ptr(), out.data_ptr(), kmask.data_ptr(), B, S, heads, hd, int(seq2seq), obj_end,
+                                         float(hd) ** -0.5, _stream())
+        _lib.check(rc, "mvlt_joint_attention_tc")
+        return out
     rc = lib.mvlt_joint_attention(qkv.data_ptr(), out.data_ptr(), _code(qkv), kmask.data_ptr(), B, S, heads, hd,
                                   int(seq2seq), obj_end, float(hd) ** -0.5, _stream())
     _lib.check(rc, "mvlt_joint_attention")

@@ -166,3 +166,78 @@ def test_row_sharded_all_gather_world2_gloo(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# HuggingFace load paths the reference's scripts use (run_vqa.py:256, run_retrieval.py:313, run_pretrain.py:190,:241) and
+# whole-model pickles (run_vqa.py:114,:264) — construction only, no kernels
+# ---------------------------------------------------------------------------------------------------------------------
+def _task_model(task, seed=0):
+    import torch
+    from medical_vision_langauge_transformer_b200.modules import config as C, model as M
+    torch.manual_seed(seed)
+    cls = {"vqa": M.MVLBertForVQA, "retrieval": M.MVLBertForRetrieval, "pretrain": M.MVLBertForPretraining}[task]
+    return cls(C.offline_config(task)).eval()
+
+
+def test_fresh_construction_keeps_pytorch_default_init():
+    """the reference never calls init_weights() (model.py:365): nn.Embedding ~ N(0,1), not N(0, 0.02)"""
+    m = _task_model("retrieval")
+    assert abs(m.MVLBert.word_embeddings.weight.std().item() - 1.0) < 0.02
+    assert hasattr(m, "all_tied_weights_keys")          # post_init() ran
+
+
+@pytest.mark.parametrize("task", ["vqa", "retrieval", "pretrain"])
+def test_save_pretrained_from_pretrained_round_trip(tmp_path, task):
+    import torch
+    m = _task_model(task)
+    m.save_pretrained(tmp_path)
+    m2 = type(m).from_pretrained(tmp_path)
+    sd1, sd2 = m.state_dict(), m2.state_dict()
+    assert list(sd1) == list(sd2)
+    for k in sd1:
+        assert torch.equal(sd1[k], sd2[k]), k
+
+
+def test_pretraining_checkpoint_into_vqa_model(tmp_path):
+    """run_vqa.py:253-256: keys the checkpoint lacks (final_mlp) are initialised as model.py:280-294 does, the rest loads"""
+    import torch
+    from medical_vision_langauge_transformer_b200.modules import config as C, model as M
+    pm = _task_model("pretrain", seed=1)
+    pm.save_pretrained(tmp_path)
+    v = M.MVLBertForVQA.from_pretrained(tmp_path, config=C.offline_config("vqa"))
+    sdp, sdv = pm.state_dict(), v.state_dict()
+    shared = [k for k in sdv if k in sdp]
+    assert len(shared) > 500 and all(torch.equal(sdp[k], sdv[k]) for k in shared)
+    w, b = sdv["final_mlp.1.weight"], sdv["final_mlp.1.bias"]
+    assert torch.isfinite(w).all() and 0.015 < w.std().item() < 0.025 and b.abs().max().item() == 0
+
+
+def test_whole_model_pickle_round_trip(tmp_path):
+    import torch
+    m = _task_model("vqa")
+    torch.save(m, tmp_path / "model.pt")
+    m2 = torch.load(tmp_path / "model.pt", weights_only=False)
+    assert type(m2) is type(m)
+    sd1, sd2 = m.state_dict(), m2.state_dict()
+    assert list(sd1) == list(sd2) and all(torch.equal(sd1[k], sd2[k]) for k in sd1)
+
+
+def test_train_mode_is_refused_not_silently_eval():
+    import torch
+    m = _task_model("vqa")
+    m.train()
+    with pytest.raises(NotImplementedError, match="eval"):
+        m.conv.conv[0].forward_features(torch.zeros(1, 3, 224, 224))
+    with pytest.raises(NotImplementedError, match="eval"):
+        m.MVLBert.encode(torch.zeros(1, 80, dtype=torch.long), None, torch.zeros(1, 49, 768))
+
+
+def test_vit_mlp_accepts_old_torchvision_keys():
+    import torch
+    from medical_vision_langauge_transformer_b200.modules.visual_feature_extractor import _ViTMLP
+    mlp = _ViTMLP(8, 16)
+    sd = {"linear_1.weight": torch.randn(16, 8), "linear_1.bias": torch.randn(16), "linear_2.weight": torch.randn(8, 16),
+          "linear_2.bias": torch.randn(8)}
+    mlp.load_state_dict(dict(sd), strict=True)
+    assert torch.equal(mlp[0].weight, sd["linear_1.weight"]) and torch.equal(mlp[3].bias, sd["linear_2.bias"])

@@ -255,6 +255,97 @@ def test_window_attention(cuda, H, C, heads, shift):
     assert relerr(out16.cpu(), ref) < 1.5e-2
 
 
+@pytest.mark.parametrize("H,C,heads", [(56, 96, 3), (28, 192, 6), (14, 384, 12), (7, 768, 24)])
+@pytest.mark.parametrize("shift", [0, 3])
+def test_window_attention_tc(cuda, H, C, heads, shift):
+    """tcgen05 window attention: qkv rows window-major (the order layernorm_winmajor + the qkv GEMM produce), output natural."""
+    from medical_vision_langauge_transformer_b200 import ops
+    if H == 7 and shift:
+        pytest.skip("stage 3 never shifts (vfe.py:302-305)")
+    B, qkv, relb, ref = _window_case(H, C, heads, shift, seed=H + shift)
+    perm = ops.window_major_index(B, H, H, 7, shift, device="cuda")
+    qkv_wm = torch.empty_like(qkv)
+    qkv_wm[perm] = qkv
+    table = ops.window_bias_table(relb, shift)
+    out16 = ops.window_attention_tc(qkv_wm.bfloat16().contiguous(), table, B, H, H, C, heads, 7, shift, 32 ** -0.5)
+    assert relerr(out16.cpu(), ref) < 1.5e-2
+    # against the same arithmetic on the bf16-rounded operands: only P's bf16 rounding and the fp32 sums differ
+    out_ref16 = ops.window_attention(qkv.bfloat16().float(), relb, B, H, H, C, heads, 7, shift, 32 ** -0.5)
+    assert relerr(out16, out_ref16) < 6e-3
+
+
+@pytest.mark.parametrize("B,H,C,heads,shift", [(1, 7, 768, 24, 0), (3, 7, 768, 24, 0), (5, 14, 384, 12, 3), (64, 14, 384, 12, 3),
+                                              (64, 14, 384, 12, 0), (16, 56, 96, 3, 3), (33, 28, 192, 6, 3)])
+def test_window_attention_tc_batches(cuda, B, H, C, heads, shift):
+    """odd window counts (a tile with one window), many tiles per CTA (slot reuse), every stage geometry; checked against
+    the fp32 kernel on the bf16-rounded operands."""
+    from medical_vision_langauge_transformer_b200 import ops
+    qkv = rnd(B * H * H, 3 * C, seed=B + H).bfloat16()
+    relb = torch.zeros(heads, 64, 64, device="cuda")
+    relb[:, :49, :49] = rnd(heads, 49, 49, seed=7, scale=0.5)
+    ref = ops.window_attention(qkv.float(), relb, B, H, H, C, heads, 7, shift, 32 ** -0.5)
+    perm = ops.window_major_index(B, H, H, 7, shift, device="cuda")
+    qkv_wm = torch.empty_like(qkv)
+    qkv_wm[perm] = qkv
+    out = ops.window_attention_tc(qkv_wm, ops.window_bias_table(relb, shift), B, H, H, C, heads, 7, shift, 32 ** -0.5)
+    assert torch.isfinite(out.float()).all()
+    assert relerr(out, ref) < 6e-3
+    out2 = ops.window_attention_tc(qkv_wm, ops.window_bias_table(relb, shift), B, H, H, C, heads, 7, shift, 32 ** -0.5)
+    assert torch.equal(out, out2), "run-to-run bit reproducibility"
+
+
+@pytest.mark.parametrize("B,H,C,shift", [(2, 56, 96, 0), (2, 56, 96, 3), (3, 28, 192, 3), (2, 14, 384, 3), (5, 7, 768, 0)])
+def test_layernorm_winmajor(cuda, B, H, C, shift):
+    from medical_vision_langauge_transformer_b200 import ops
+    x = rnd(B * H * H, C, seed=3)
+    g, b = 1 + rnd(C, seed=4, scale=0.1), rnd(C, seed=5, scale=0.1)
+    nat = ops.layernorm(x, g, b, 1e-5, torch.bfloat16)
+    wm = ops.layernorm_winmajor(x, g, b, 1e-5, B, H, H, 7, shift)
+    perm = ops.window_major_index(B, H, H, 7, shift, device="cuda")
+    assert torch.equal(wm[perm], nat)
+    # the index map is the reference's roll + window_partition
+    from oracle import mvlt_oracle as O
+    tok = torch.arange(B * H * H, dtype=torch.float32).view(B, H, H, 1)
+    if shift:
+        tok = torch.roll(tok, (-shift, -shift), (1, 2))
+    order = O.window_partition(tok, 7).reshape(-1).long()          # window-major position -> natural token
+    assert torch.equal(perm.cpu()[order], torch.arange(B * H * H))
+
+
+def test_patch_embed_window_major_norm(cuda):
+    from medical_vision_langauge_transformer_b200 import ops
+    B = 3
+    img = rnd(B, 3, 224, 224, seed=1, scale=0.02)
+    w, b = rnd(96, 3, 4, 4, seed=2, scale=0.1), rnd(96, seed=3, scale=0.1)
+    g, be = 1 + rnd(96, seed=4, scale=0.1), rnd(96, seed=5, scale=0.1)
+    g2, be2 = 1 + rnd(96, seed=6, scale=0.1), rnd(96, seed=7, scale=0.1)
+    out, nat = ops.patch_embed_ln(img, w, b, g, be, 1e-5, tensor_cores=True, next_norm=(g2, be2, 1e-5))
+    out_w, wm = ops.patch_embed_ln(img, w, b, g, be, 1e-5, tensor_cores=True, next_norm=(g2, be2, 1e-5), next_norm_window=7)
+    assert torch.equal(out, out_w)
+    perm = ops.window_major_index(B, 56, 56, 7, 0, device="cuda")
+    assert torch.equal(wm[perm], nat)
+
+
+@pytest.mark.parametrize("B,S", [(3, 131), (64, 131), (1, 131), (7, 74), (64, 74), (5, 81), (2, 96), (2, 64), (3, 128), (3, 144)])
+@pytest.mark.parametrize("seq2seq", [False, True])
+def test_joint_attention_tc(cuda, B, S, seq2seq):
+    """tcgen05 joint attention (tiles of 128 consecutive rows spanning several samples under the lane mask) against the fp32
+    kernel on the bf16-rounded operands, with ragged key masks."""
+    from medical_vision_langauge_transformer_b200 import ops
+    heads, D = 12, 768
+    qkv = rnd(B * S, 3 * D, seed=S + B).bfloat16()
+    g = torch.Generator().manual_seed(S)
+    valid = torch.randint(52, S + 1, (B,), generator=g)
+    kmask = torch.where(torch.arange(S)[None] < valid[:, None], 0.0, -10000.0).float().cuda().contiguous()
+    ref = ops.joint_attention(qkv.float(), kmask, B, S, heads, seq2seq, 50)
+    out = ops.joint_attention(qkv, kmask, B, S, heads, seq2seq, 50, impl="tc")
+    assert torch.isfinite(out.float()).all()
+    assert relerr(out, ref) < 6e-3
+    old = ops.joint_attention(qkv, kmask, B, S, heads, seq2seq, 50, impl="warp")
+    assert relerr(out, old) < 6e-3
+    assert torch.equal(out, ops.joint_attention(qkv, kmask, B, S, heads, seq2seq, 50, impl="tc")), "run-to-run bit reproducibility"
+
+
 @pytest.mark.parametrize("L", [80, 23, 30, 1])
 @pytest.mark.parametrize("seq2seq", [False, True])
 def test_joint_embed_and_attention(cuda, L, seq2seq):
