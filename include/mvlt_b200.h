@@ -145,6 +145,15 @@ int mvlt_patch_merge_ln(const float* x, void* out, int out_dtype, const float* g
 int mvlt_window_attention(const void* qkv, void* out, int dtype, const float* relbias, int B, int H, int W, int C,
                           int heads, int window, int shift, float scale, mvlt_stream_t stream);
 
+/* Second half of a Swin block in ONE tcgen05 kernel on CTA pairs (cta_group::2), in place on the fp32 residual stream x [M, C]:
+ *   x <- x + o . w_proj^T + b_proj (vfe.py:252, :384), then x <- x + fc2(GELU(fc1(LayerNorm(x)))) (vfe.py:385, :136-139).
+ * o = window-attention output, bf16 [M, C] dense, or NULL (MLP half only; w_proj / b_proj ignored).  The new residual rows stay
+ * in tensor memory between the two halves; x is read once and written once.  Weights bf16 in nn.Linear layout (w_proj [C, C],
+ * w1 [4C, C], w2 [C, 4C]); biases and LayerNorm parameters fp32, 16-byte aligned.  C in {192, 384}, hidden == 4C. */
+int mvlt_swin_block_tail(const void* o, float* x, long long ldx, const void* w_proj, const float* b_proj, const float* gamma,
+                         const float* beta, float eps, const void* w1, const float* b1, const void* w2, const float* b2,
+                         long long M, int C, int hidden, mvlt_stream_t stream);
+
 /* The same attention on tcgen05 / TMEM / TMA (bf16): qkv [B*nW*49, 3C] with rows WINDOW-MAJOR for this block's shift (as
  * written by mvlt_layernorm_rows_winmajor + the qkv GEMM), out [B*H*W, C] in NATURAL token order (window_reverse + the
  * reverse roll of vfe.py:159-173, :373-381 are the output scatter).  Two windows per 128-lane accumulator tile, S = Q.K^T

@@ -50,20 +50,23 @@ __device__ __forceinline__ float at_ex2(float x) {
 // =====================================================================================================================
 // Swin window attention
 // =====================================================================================================================
-constexpr int WT_SLOTS = 4;
+constexpr int WT_SLOTS = 4;                      // tiles in flight in tensor memory (128 columns each) = softmax warpgroups
+constexpr int WT_STAGES = 7;                     // operand stages in shared memory: the TMA producer runs this many tiles ahead
 constexpr int WT_THREADS = (2 + 4 * WT_SLOTS) * 32;
 constexpr int WT_MAT = 128 * 64;                 // one operand matrix: 128 rows x 32 bf16 (window a: rows 0.., window b: rows 64..)
 constexpr int WT_SLOT_BYTES = 3 * WT_MAT;        // Q | K | V
 constexpr int WT_WIN_BYTES = 49 * 64;            // one TMA box
 constexpr int WT_BIAS_LD = 52;                   // floats per bias row (49 + pad: 16-byte aligned rows, conflict-free LDS.128)
 constexpr int WT_BIAS_CLS = 49 * WT_BIAS_LD;
-constexpr int WT_SMEM = WT_SLOTS * WT_SLOT_BYTES + 4 * WT_BIAS_CLS * 4 + 6 * WT_SLOTS * 8 + 16 + 1024;
+constexpr int WT_SMEM = WT_STAGES * WT_SLOT_BYTES + 4 * WT_BIAS_CLS * 4 + (2 * WT_STAGES + 4 * WT_SLOTS) * 8 + 16 + 1024;
+static_assert(WT_SMEM <= 227 * 1024, "shared memory budget");
 
 struct WinTcParams {
   bf16* out;            // [B*H*W, C] natural token order
   const float* bias;    // [n_cls][heads][49][52] = (rel-pos bias + shift mask) * log2e
   int H, W, C, heads, shift, nWh, nWw, n_cls;
   int n_windows, n_pairs, n_groups;
+  int nW_shift, nWw_shift;   // log2 of windows per image / per window row when both are powers of two (Swin at 224), else -1
   float scale_log2e;
 };
 
@@ -73,15 +76,15 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const WinTcP
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* opnd = smem;
-  float* bias_s = reinterpret_cast<float*>(smem + WT_SLOTS * WT_SLOT_BYTES);
+  float* bias_s = reinterpret_cast<float*>(smem + WT_STAGES * WT_SLOT_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 4 * WT_BIAS_CLS);
-  uint64_t* full = bars;                       // TMA -> MMA
-  uint64_t* empty = bars + WT_SLOTS;           // P.V retired -> TMA (operands of the slot are free)
-  uint64_t* s_full = bars + 2 * WT_SLOTS;      // Q.K^T retired -> softmax warpgroup
-  uint64_t* p_full = bars + 3 * WT_SLOTS;      // P written (4 warp arrivals) -> MMA
-  uint64_t* o_full = bars + 4 * WT_SLOTS;      // P.V retired -> epilogue
-  uint64_t* o_empty = bars + 5 * WT_SLOTS;     // O read (4 warp arrivals) -> MMA may overwrite the slot's TMEM columns
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6 * WT_SLOTS);
+  uint64_t* full = bars;                                   // [STAGES] TMA -> MMA
+  uint64_t* empty = bars + WT_STAGES;                      // [STAGES] P.V retired -> TMA (the stage's operands are free)
+  uint64_t* s_full = bars + 2 * WT_STAGES;                 // [SLOTS] Q.K^T retired -> softmax warpgroup
+  uint64_t* p_full = s_full + WT_SLOTS;                    // [SLOTS] P written (4 warp arrivals) -> MMA
+  uint64_t* o_full = p_full + WT_SLOTS;                    // [SLOTS] P.V retired -> epilogue
+  uint64_t* o_empty = o_full + WT_SLOTS;                   // [SLOTS] O read (4 warp arrivals) -> MMA may overwrite the slot's columns
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_empty + WT_SLOTS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.x % p.heads, group = blockIdx.x / p.heads;
@@ -89,12 +92,14 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const WinTcP
 
   // operand slots start zeroed: rows 49..63 of each window half are never written by TMA and the V rows among them are
   // multiplied (by P = 0) in the second MMA
-  for (int i = threadIdx.x; i < WT_SLOTS * WT_SLOT_BYTES / 16; i += WT_THREADS) reinterpret_cast<uint4*>(opnd)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < WT_STAGES * WT_SLOT_BYTES / 16; i += WT_THREADS) reinterpret_cast<uint4*>(opnd)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
+    // a stage is free once P.V has retired (1 commit arrival) AND the four epilogue warps have flushed the output tile they
+    // parked in its Q rows (4 arrivals)
+    for (int s = 0; s < WT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 5); }
     for (int s = 0; s < WT_SLOTS; ++s) {
-      mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 4); mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 4);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4); mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 4);
     }
     mbar_fence_init();
   }
@@ -120,17 +125,17 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const WinTcP
   if (warp == 0) {
     // ------------------------------- TMA producer ---------------------------------------------------------------------
     for (int n = 0; n < my_tiles; ++n) {
-      const int slot = n % WT_SLOTS, u = n / WT_SLOTS;
-      mbar_wait(&empty[slot], (u & 1) ^ 1);
+      const int st = n % WT_STAGES, u = n / WT_STAGES;
+      mbar_wait(&empty[st], (u & 1) ^ 1);
       const int w0 = 2 * (group + n * p.n_groups);
       const int nvalid = p.n_windows - w0 >= 2 ? 2 : 1;
       if (elect_one()) {
-        mbar_arrive_expect_tx(&full[slot], (uint32_t)(nvalid * 3 * WT_WIN_BYTES));
-        uint8_t* dst = opnd + slot * WT_SLOT_BYTES;
+        mbar_arrive_expect_tx(&full[st], (uint32_t)(nvalid * 3 * WT_WIN_BYTES));
+        uint8_t* dst = opnd + st * WT_SLOT_BYTES;
         for (int hf = 0; hf < nvalid; ++hf)
 #pragma unroll
           for (int m = 0; m < 3; ++m)
-            tma_load_2d(dst + m * WT_MAT + hf * 4096, &tmap_qkv, &full[slot], m * p.C + head * 32, (w0 + hf) * 49);
+            tma_load_2d(dst + m * WT_MAT + hf * 4096, &tmap_qkv, &full[st], m * p.C + head * 32, (w0 + hf) * 49);
       }
       __syncwarp();
     }
@@ -148,9 +153,10 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const WinTcP
       for (int slot = 0; slot < WT_SLOTS; ++slot) {
         const uint32_t n_slot = my_tiles > slot ? (uint32_t)((my_tiles - slot + WT_SLOTS - 1) / WT_SLOTS) : 0u;
         const uint32_t tm = tmem_base + slot * 128;
-        const uint32_t sm = base + slot * WT_SLOT_BYTES;
         if (pv_cnt[slot] < s_cnt[slot]) {
           const uint32_t u = pv_cnt[slot];
+          const uint32_t n = slot + u * WT_SLOTS, st = n % WT_STAGES;          // tile -> operand stage
+          const uint32_t sm = base + st * WT_SLOT_BYTES;
           if (__any_sync(0xffffffffu, mbar_test(&p_full[slot], u & 1))) {
             tc_fence_after();
             if (elect_one()) {
@@ -159,14 +165,16 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const WinTcP
               for (int k = 0; k < 4; ++k)
                 umma_bf16_ts_masked(tm + 64, tm + 8 * k, umma_desc(sm + 2 * WT_MAT + 1024 * k, 4096, 512, UMMA_SW64), id_o, k, 0, 0, 0, 0);
               umma_commit(&o_full[slot]);
-              umma_commit(&empty[slot]);
+              umma_commit(&empty[st]);
             }
             __syncwarp();
             ++pv_cnt[slot]; --remaining; progressed = true;
           }
         } else if (s_cnt[slot] < n_slot) {
           const uint32_t u = s_cnt[slot];
-          if (__any_sync(0xffffffffu, mbar_test(&o_empty[slot], (u & 1) ^ 1) && mbar_test(&full[slot], u & 1))) {
+          const uint32_t n = slot + u * WT_SLOTS, st = n % WT_STAGES;
+          const uint32_t sm = base + st * WT_SLOT_BYTES;
+          if (__any_sync(0xffffffffu, mbar_test(&o_empty[slot], (u & 1) ^ 1) && mbar_test(&full[st], (n / WT_STAGES) & 1))) {
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
@@ -196,14 +204,20 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const WinTcP
       const int w = 2 * (group + n * p.n_groups) + half;
       const bool valid = w < p.n_windows && i < 49;
       const int wc = w < p.n_windows ? w : p.n_windows - 1;
-      const int b = wc / nW, win = wc - b * nW;
-      const int wh = win / p.nWw, ww = win - wh * p.nWw;
+      int b, win, wh, ww;
+      if (p.nW_shift >= 0) {          // Swin at 224: 64 / 16 / 4 / 1 windows per image — shifts instead of divisions
+        b = wc >> p.nW_shift; win = wc & (nW - 1);
+        wh = win >> p.nWw_shift; ww = win & (p.nWw - 1);
+      } else {
+        b = wc / nW; win = wc - b * nW;
+        wh = win / p.nWw; ww = win - wh * p.nWw;
+      }
       // window class of the shift mask (vfe.py:321-339): windows of the last window row / column straddle the roll seam
       const int cls = p.shift > 0 ? ((wh == p.nWh - 1 ? 2 : 0) | (ww == p.nWw - 1 ? 1 : 0)) : 0;
       int hh = wh * 7 + ri + p.shift, xx = ww * 7 + ci + p.shift;     // torch.roll(-shift) then partition == read at +shift
       if (hh >= p.H) hh -= p.H;
       if (xx >= p.W) xx -= p.W;
-      const long long tok = ((long long)b * p.H + hh) * p.W + xx;
+      const int tok = valid ? (b * p.H + hh) * p.W + xx : -1;     // output row in natural token order (n_windows * 49 < 2^31)
       const float* brow = bias_s + (cls * 49 + ib) * WT_BIAS_LD;
 
       mbar_wait(&s_full[slot], u & 1);
@@ -260,14 +274,32 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const WinTcP
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[slot]);
-      if (valid) {   // window_reverse + roll back == scatter through the index map: 64 contiguous bytes per (token, head)
-        uint4* dst = reinterpret_cast<uint4*>(p.out + tok * p.C + head * 32);
+      // window_reverse + roll back == scatter through the index map.  The warp's 32 x 32 output tile is parked in the Q rows of
+      // the tile's operand stage (dead since Q.K^T retired; same 64-byte rows, same swizzle) and leaves as four stores in
+      // which every group of 4 lanes writes one token's 64 contiguous bytes
+      {
+        const int stg_n = n % WT_STAGES;
+        uint8_t* q_rows = opnd + stg_n * WT_SLOT_BYTES + (quarter * 32) * 64;
+        const uint32_t swz = ((uint32_t)lane >> 1) & 3u;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          dst[q] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * q]) * inv, __uint_as_float(o[8 * q + 1]) * inv),
-                              pack_bf16x2(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv),
-                              pack_bf16x2(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv),
-                              pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv));
+          *reinterpret_cast<uint4*>(q_rows + lane * 64 + (((uint32_t)q ^ swz) << 4)) =
+              make_uint4(pack_bf16x2(__uint_as_float(o[8 * q]) * inv, __uint_as_float(o[8 * q + 1]) * inv),
+                         pack_bf16x2(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv),
+                         pack_bf16x2(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv),
+                         pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv));
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + (lane >> 2), cc = lane & 3;
+          const int tk = __shfl_sync(0xffffffffu, tok, rr);
+          const uint4 v = *reinterpret_cast<const uint4*>(q_rows + rr * 64 + (((uint32_t)cc ^ (((uint32_t)rr >> 1) & 3u)) << 4));
+          if (tk >= 0) *reinterpret_cast<uint4*>(p.out + (long long)tk * p.C + head * 32 + cc * 8) = v;
+        }
+        __syncwarp();
+        // rows 49..63 of each half must read as zero again when the stage is reused as V? no: this is the Q matrix, whose pad
+        // rows only feed unused score rows — nothing to restore.  Release the stage.
+        if (lane == 0) mbar_arrive(&empty[stg_n]);
       }
     }
   }
@@ -284,14 +316,17 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const WinTcP
 // BERT joint attention (head_dim 64)
 // =====================================================================================================================
 constexpr int JT_SLOTS = 2;
-constexpr int JT_THREADS = (2 + 4 * JT_SLOTS) * 32;
+constexpr int JT_SOFTMAX_WARP0 = 3;              // warp 0: Q / K producer, warp 1: MMA issuer, warp 2: V producer
+constexpr int JT_THREADS = (JT_SOFTMAX_WARP0 + 4 * JT_SLOTS) * 32;
 constexpr int JT_Q_BYTES = 128 * 128;
 
 template <int SP, int NS> struct JtPlan {
   static constexpr int KV_BYTES = SP * 128;
-  static constexpr int SLOT_BYTES = JT_Q_BYTES + 2 * NS * KV_BYTES;
+  static constexpr int QK_BYTES = JT_Q_BYTES + NS * KV_BYTES;     // released as soon as Q.K^T has retired
+  static constexpr int V_BYTES = NS * KV_BYTES;                   // released when P.V has retired
   static constexpr int MASK_FLOATS = JT_SLOTS * NS * SP;
-  static constexpr int SMEM = JT_SLOTS * SLOT_BYTES + MASK_FLOATS * 4 + 6 * JT_SLOTS * 8 + 16 + 1024;
+  static constexpr int STAGING_BYTES = 4 * JT_SLOTS * 4096;       // one [32 rows x 128 B] output tile per softmax warp
+  static constexpr int SMEM = JT_SLOTS * (QK_BYTES + V_BYTES) + STAGING_BYTES + MASK_FLOATS * 4 + 9 * JT_SLOTS * 8 + 16 + 1024;
   static_assert(KV_BYTES % 1024 == 0 && SP % 16 == 0 && SP <= 144, "K / V buffers are whole SWIZZLE_128B atoms; S columns + O fit 256");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -300,8 +335,12 @@ struct JointTcParams {
   bf16* out;              // [R, heads*64]
   const float* kmask;     // [B, S] additive (0 / -10000)
   int R, S, B, heads, seq2seq, obj_end, n_items;
-  float scale_log2e;
+  float scale;
+  unsigned long long* trace;   // debug: clock64 stamps of CTA 0 (tools/attn_trace.py); nullptr in production
 };
+static unsigned long long* g_attn_trace = nullptr;
+// slot t of event e of tile n (first 8 tiles of CTA 0): trace[16 + n * 16 + e]; trace[0] = kernel start
+#define JT_STAMP(n, e) do { if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && (n) < 8) p.trace[16 + (n) * 16 + (e)] = (unsigned long long)clock64(); } while (0)
 
 // bits [lo, hi) of a 128-bit lane set, word w
 __device__ __forceinline__ uint32_t jt_range_word(int lo, int hi, int w) {
@@ -313,23 +352,49 @@ __device__ __forceinline__ uint32_t jt_range_word(int lo, int hi, int w) {
   return upto_h & ~upto_l;
 }
 
+// one 32- or 16-column chunk of a score row: v_j = acc_j * scale + mask_j (the reference's units), optional seq2seq blocking
+template <int W>
+__device__ __forceinline__ void jt_scores(const uint32_t (&a)[W], float (&v)[W], const float* mrow, float scale, bool seq2seq, int j0, int i,
+                                          int obj_end) {
+  const float blocked = -10000.0f;
+#pragma unroll
+  for (int q = 0; q < W / 4; ++q) {
+    const float4 mv = *reinterpret_cast<const float4*>(mrow + j0 + 4 * q);
+    v[4 * q + 0] = fmaf(__uint_as_float(a[4 * q + 0]), scale, mv.x);
+    v[4 * q + 1] = fmaf(__uint_as_float(a[4 * q + 1]), scale, mv.y);
+    v[4 * q + 2] = fmaf(__uint_as_float(a[4 * q + 2]), scale, mv.z);
+    v[4 * q + 3] = fmaf(__uint_as_float(a[4 * q + 3]), scale, mv.w);
+  }
+  if (seq2seq) {   // model.py:118-123: text rows see the image block and the text up to themselves
+#pragma unroll
+    for (int c = 0; c < W; ++c)
+      if (j0 + c > i && j0 + c > obj_end) v[c] += blocked;
+  }
+}
+
 template <int SP, int NS>
 __global__ void __launch_bounds__(JT_THREADS, 1)
-joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const JointTcParams p) {
+joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                     const __grid_constant__ CUtensorMap tmap_out, const JointTcParams p) {
   using P = JtPlan<SP, NS>;
-  constexpr int KV = P::KV_BYTES, SLOT = P::SLOT_BYTES;
+  constexpr int KV = P::KV_BYTES, QKB = P::QK_BYTES, VB = P::V_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  float* mask_s = reinterpret_cast<float*>(smem + JT_SLOTS * SLOT);
+  uint8_t* smem_v = smem + JT_SLOTS * QKB;
+  uint8_t* staging = smem_v + JT_SLOTS * VB;       // 1024-byte aligned: QKB and VB are multiples of 1024
+  float* mask_s = reinterpret_cast<float*>(staging + P::STAGING_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(mask_s + P::MASK_FLOATS);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + JT_SLOTS;
-  uint64_t* s_full = bars + 2 * JT_SLOTS;
-  uint64_t* p_full = bars + 3 * JT_SLOTS;
-  uint64_t* o_full = bars + 4 * JT_SLOTS;
-  uint64_t* o_empty = bars + 5 * JT_SLOTS;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6 * JT_SLOTS);
+  uint64_t* qk_full = bars;                      // TMA (Q, K) -> MMA
+  uint64_t* qk_empty = bars + JT_SLOTS;          // Q.K^T retired -> Q / K producer
+  uint64_t* v_full = bars + 2 * JT_SLOTS;        // TMA (V) -> MMA
+  uint64_t* v_empty = bars + 3 * JT_SLOTS;       // P.V retired -> V producer
+  uint64_t* s_full = bars + 4 * JT_SLOTS;        // Q.K^T retired -> softmax warpgroup
+  uint64_t* p_full = bars + 5 * JT_SLOTS;        // P written (4 warp arrivals) -> MMA
+  uint64_t* o_full = bars + 6 * JT_SLOTS;        // P.V retired -> epilogue
+  uint64_t* o_empty = bars + 7 * JT_SLOTS;       // O read (4 warp arrivals) -> MMA may overwrite the slot's TMEM columns
+  uint64_t* m_full = bars + 8 * JT_SLOTS;        // key masks of the slot's tile staged by the V-producer warp -> softmax warpgroup
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9 * JT_SLOTS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int my_tiles = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -338,9 +403,11 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_kv);
+    tma_prefetch_desc(&tmap_out);
     for (int s = 0; s < JT_SLOTS; ++s) {
-      mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 4); mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 4);
+      mbar_init(&qk_full[s], 1); mbar_init(&qk_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4); mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 4);
+      mbar_init(&m_full[s], 32);                  // every lane of the V-producer warp: cp.async.mbarrier.arrive.noinc
     }
     mbar_fence_init();
   }
@@ -348,11 +415,14 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
   }
+  // key-mask rows start as 0 for the keys of a sequence and "minus infinity" past S; the per-tile copies only touch j < S
+  for (int i = threadIdx.x; i < P::MASK_FLOATS; i += JT_THREADS) mask_s[i] = (i % SP) < p.S ? 0.f : AT_NEG_BIG;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_grid_sync();
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[0] = (unsigned long long)clock64();
 
   // item n of this CTA -> (row tile, head): heads vary fastest, so the CTAs of a wave share the row tile's K / V rows in L2
   auto item_of = [&](int n, int& row0, int& head, int& b0, int& ns) {
@@ -365,23 +435,53 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   };
 
   if (warp == 0) {
-    // ------------------------------- TMA producer ---------------------------------------------------------------------
+    // ------------------------------- TMA producer: Q and K (their buffers are recycled as soon as Q.K^T has retired, so
+    // the next tile of the slot is resident long before the softmax of the current one ends) --------------------------
     for (int n = 0; n < my_tiles; ++n) {
       const int slot = n % JT_SLOTS, u = n / JT_SLOTS;
       int row0, head, b0, ns;
       item_of(n, row0, head, b0, ns);
-      mbar_wait(&empty[slot], (u & 1) ^ 1);
+      mbar_wait(&qk_empty[slot], (u & 1) ^ 1);
+      JT_STAMP(n, 0);
       if (elect_one()) {
-        uint8_t* dst = smem + slot * SLOT;
-        mbar_arrive_expect_tx(&full[slot], (uint32_t)(JT_Q_BYTES + ns * 2 * KV));
-        tma_load_2d(dst, &tmap_q, &full[slot], head * 64, row0);                 // rows past R arrive as zeros
-        for (int k = 0; k < ns; ++k) {
-          // SP rows from the sample's first row: the rows past S belong to the next sample (finite, masked) or are zero fill
-          tma_load_2d(dst + JT_Q_BYTES + k * KV, &tmap_kv, &full[slot], C + head * 64, (b0 + k) * p.S);
-          tma_load_2d(dst + JT_Q_BYTES + (NS + k) * KV, &tmap_kv, &full[slot], 2 * C + head * 64, (b0 + k) * p.S);
-        }
+        uint8_t* dst = smem + slot * QKB;
+        mbar_arrive_expect_tx(&qk_full[slot], (uint32_t)(JT_Q_BYTES + ns * KV));
+        tma_load_2d(dst, &tmap_q, &qk_full[slot], head * 64, row0);                 // rows past R arrive as zeros
+        // SP rows from the sample's first row: the rows past S belong to the next sample (finite, masked) or are zero fill
+        for (int k = 0; k < ns; ++k) tma_load_2d(dst + JT_Q_BYTES + k * KV, &tmap_kv, &qk_full[slot], C + head * 64, (b0 + k) * p.S);
       }
       __syncwarp();
+    }
+  } else if (warp == 2) {
+    // ------------------------------- TMA producer: V; it also stages the additive key masks of the tile's samples (log2
+    // units, keys past S = "minus infinity") one tile ahead of the softmax warps.  v_empty of the slot implies that P.V of
+    // its previous tile has retired, i.e. every reader of the previous masks is done. ------------------------------------
+    const bool s2s_ = p.seq2seq != 0;
+    for (int n = 0; n < my_tiles; ++n) {
+      const int slot = n % JT_SLOTS, u = n / JT_SLOTS;
+      int row0, head, b0, ns;
+      item_of(n, row0, head, b0, ns);
+      mbar_wait(&v_empty[slot], (u & 1) ^ 1);
+      JT_STAMP(n, 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&v_full[slot], (uint32_t)(ns * KV));
+        for (int k = 0; k < ns; ++k) tma_load_2d(smem_v + slot * VB + k * KV, &tmap_kv, &v_full[slot], 2 * C + head * 64, (b0 + k) * p.S);
+      }
+      __syncwarp();
+      // additive key masks (0 / -10000, model.py:126) of the tile's samples: asynchronous 4-byte global -> shared copies (no
+      // registers, all in flight at once); their completion arrives on m_full.  seq2seq: the rows stay 0 (mask is positional)
+      float* msk = mask_s + slot * NS * SP;
+      if (!s2s_) {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+          const int bb = b0 + k;
+          if (bb < p.B)
+            for (int j = lane; j < p.S; j += 32)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(msk + k * SP + j)), "l"(p.kmask + (long long)bb * p.S + j) : "memory");
+        }
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&m_full[slot])) : "memory");
+      JT_STAMP(n, 4);
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -----------------------------------------------------------------------
@@ -397,16 +497,17 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       for (int slot = 0; slot < JT_SLOTS; ++slot) {
         const uint32_t n_slot = my_tiles > slot ? (uint32_t)((my_tiles - slot + JT_SLOTS - 1) / JT_SLOTS) : 0u;
         const uint32_t tm = tmem_base + slot * 256;
-        const uint32_t sm = base + slot * SLOT;
+        const uint32_t sm_qk = base + slot * QKB, sm_v = base + JT_SLOTS * QKB + slot * VB;
         const bool do_pv = pv_cnt[slot] < s_cnt[slot];
         if (!do_pv && s_cnt[slot] >= n_slot) continue;
         const uint32_t u = do_pv ? pv_cnt[slot] : s_cnt[slot];
-        const bool ready = do_pv ? mbar_test(&p_full[slot], u & 1)
-                                 : (mbar_test(&o_empty[slot], (u & 1) ^ 1) && mbar_test(&full[slot], u & 1));
+        const bool ready = do_pv ? (mbar_test(&p_full[slot], u & 1) && mbar_test(&v_full[slot], u & 1))
+                                 : (mbar_test(&o_empty[slot], (u & 1) ^ 1) && mbar_test(&qk_full[slot], u & 1));
         if (!__any_sync(0xffffffffu, ready)) continue;
         tc_fence_after();
         int row0, head, b0, ns;
         item_of(slot + (int)u * JT_SLOTS, row0, head, b0, ns);
+        JT_STAMP(slot + (int)u * JT_SLOTS, do_pv ? 3 : 2);
         if (elect_one()) {
           for (int k = 0; k < ns; ++k) {
             // lanes of this tile that belong to sample b0 + k; every other lane is disabled for this sample's products
@@ -416,20 +517,20 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             if (!do_pv) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                umma_bf16_masked(tm, umma_desc(sm + 32 * ks, 16, 1024, UMMA_SW128),
-                                 umma_desc(sm + JT_Q_BYTES + k * KV + 32 * ks, 16, 1024, UMMA_SW128), id_s, ks, d0, d1, d2, d3);
+                umma_bf16_masked(tm, umma_desc(sm_qk + 32 * ks, 16, 1024, UMMA_SW128),
+                                 umma_desc(sm_qk + JT_Q_BYTES + k * KV + 32 * ks, 16, 1024, UMMA_SW128), id_s, ks, d0, d1, d2, d3);
             } else {
 #pragma unroll
               for (int ks = 0; ks < SP / 16; ++ks)
-                umma_bf16_ts_masked(tm + 192, tm + 8 * ks, umma_desc(sm + JT_Q_BYTES + (NS + k) * KV + 2048 * ks, 16, 1024, UMMA_SW128),
-                                    id_o, ks, d0, d1, d2, d3);
+                umma_bf16_ts_masked(tm + 192, tm + 8 * ks, umma_desc(sm_v + k * KV + 2048 * ks, 16, 1024, UMMA_SW128), id_o, ks, d0, d1, d2, d3);
             }
           }
           if (do_pv) {
             umma_commit(&o_full[slot]);
-            umma_commit(&empty[slot]);
+            umma_commit(&v_empty[slot]);
           } else {
             umma_commit(&s_full[slot]);
+            umma_commit(&qk_empty[slot]);
           }
         }
         __syncwarp();
@@ -442,13 +543,14 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
   } else {
     // ------------------------------- softmax + epilogue ---------------------------------------------------------------
-    const int slot = (warp - 2) >> 2;
+    const int slot = (warp - JT_SOFTMAX_WARP0) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
-    const int wg_tid = ((warp - 2) & 3) * 32 + lane;
     const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 256;
     float* msk = mask_s + slot * NS * SP;
-    const float blocked = -10000.0f * AT_LOG2E;
+    uint8_t* stg = staging + (warp - JT_SOFTMAX_WARP0) * 4096;     // this warp's output tile: 32 rows x 128 B, SWIZZLE_128B
+    const uint32_t stg_row = (uint32_t)lane * 128u, stg_swz = (uint32_t)lane & 7u;
+    const bool s2s = p.seq2seq != 0;
     for (int n = slot, u = 0; n < my_tiles; n += JT_SLOTS, ++u) {
       int row0, head, b0, ns;
       item_of(n, row0, head, b0, ns);
@@ -456,107 +558,69 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const bool valid = g < p.R;
       const int b = valid ? g / p.S : b0;
       const int i = g - b * p.S;                         // position of this row in its sample
-      // additive key masks of the tile's samples in log2 units; keys past S get "minus infinity".  The previous readers of
-      // this buffer are done: nobody passes o_full of the previous tile before all four warps have arrived on its p_full
-      for (int idx = wg_tid; idx < NS * SP; idx += 128) {
-        const int k = idx / SP, j = idx - k * SP, bb = b0 + k;
-        float v = AT_NEG_BIG;
-        if (j < p.S && bb < p.B) v = p.seq2seq ? 0.f : __ldg(p.kmask + (long long)bb * p.S + j) * AT_LOG2E;
-        msk[idx] = v;
-      }
-      named_bar_sync(1 + slot, 128);
       const float* mrow = msk + (b - b0) * SP;
+      mbar_wait(&m_full[slot], u & 1);
+      if (quarter == 0) JT_STAMP(n, 5);
 
       mbar_wait(&s_full[slot], u & 1);
       tc_fence_after();
+      if (quarter == 0) JT_STAMP(n, 6);
       // pass 1: row maximum
       float mx = AT_NEG_BIG;
 #pragma unroll
       for (int c0 = 0; c0 < SP; c0 += 32) {
         if (SP - c0 >= 32) {
           uint32_t a[32];
+          float v[32];
           tmem_ld_32x32(tl + c0, a);
           tmem_ld_wait();
+          jt_scores<32>(a, v, mrow, p.scale, s2s, c0, i, p.obj_end);
+          float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 mv = *reinterpret_cast<const float4*>(mrow + c0 + 4 * q);
-            float v0 = fmaf(__uint_as_float(a[4 * q]), p.scale_log2e, mv.x), v1 = fmaf(__uint_as_float(a[4 * q + 1]), p.scale_log2e, mv.y);
-            float v2 = fmaf(__uint_as_float(a[4 * q + 2]), p.scale_log2e, mv.z), v3 = fmaf(__uint_as_float(a[4 * q + 3]), p.scale_log2e, mv.w);
-            if (p.seq2seq) {   // model.py:118-123: text rows see the image block and the text up to themselves
-              const int j = c0 + 4 * q;
-              if (j > i && j > p.obj_end) v0 += blocked;
-              if (j + 1 > i && j + 1 > p.obj_end) v1 += blocked;
-              if (j + 2 > i && j + 2 > p.obj_end) v2 += blocked;
-              if (j + 3 > i && j + 3 > p.obj_end) v3 += blocked;
-            }
-            mx = fmaxf(mx, fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)));
-          }
+          for (int c = 4; c < 32; c += 4) { m0 = fmaxf(m0, v[c]); m1 = fmaxf(m1, v[c + 1]); m2 = fmaxf(m2, v[c + 2]); m3 = fmaxf(m3, v[c + 3]); }
+          mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
         } else {
           uint32_t a[16];
+          float v[16];
           tmem_ld_32x16(tl + c0, a);
           tmem_ld_wait();
+          jt_scores<16>(a, v, mrow, p.scale, s2s, c0, i, p.obj_end);
+          float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 mv = *reinterpret_cast<const float4*>(mrow + c0 + 4 * q);
-            float v0 = fmaf(__uint_as_float(a[4 * q]), p.scale_log2e, mv.x), v1 = fmaf(__uint_as_float(a[4 * q + 1]), p.scale_log2e, mv.y);
-            float v2 = fmaf(__uint_as_float(a[4 * q + 2]), p.scale_log2e, mv.z), v3 = fmaf(__uint_as_float(a[4 * q + 3]), p.scale_log2e, mv.w);
-            if (p.seq2seq) {
-              const int j = c0 + 4 * q;
-              if (j > i && j > p.obj_end) v0 += blocked;
-              if (j + 1 > i && j + 1 > p.obj_end) v1 += blocked;
-              if (j + 2 > i && j + 2 > p.obj_end) v2 += blocked;
-              if (j + 3 > i && j + 3 > p.obj_end) v3 += blocked;
-            }
-            mx = fmaxf(mx, fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)));
-          }
+          for (int c = 4; c < 16; c += 4) { m0 = fmaxf(m0, v[c]); m1 = fmaxf(m1, v[c + 1]); m2 = fmaxf(m2, v[c + 2]); m3 = fmaxf(m3, v[c + 3]); }
+          mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
         }
       }
-      // pass 2: exp2, row sum, P as bf16 pairs over the score columns already consumed (columns c0/2.. of chunk c0)
+      if (quarter == 0) JT_STAMP(n, 7);
+      // pass 2: exp2((v - max) * log2e), row sum, P as bf16 pairs over the score columns already consumed (columns c0/2..)
+      const float nmx = -mx * AT_LOG2E;
       float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
       for (int c0 = 0; c0 < SP; c0 += 32) {
         if (SP - c0 >= 32) {
           uint32_t a[32], pk[16];
+          float v[32];
           tmem_ld_32x32(tl + c0, a);
           tmem_ld_wait();
+          jt_scores<32>(a, v, mrow, p.scale, s2s, c0, i, p.obj_end);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 mv = *reinterpret_cast<const float4*>(mrow + c0 + 4 * q);
-            float v0 = fmaf(__uint_as_float(a[4 * q]), p.scale_log2e, mv.x - mx), v1 = fmaf(__uint_as_float(a[4 * q + 1]), p.scale_log2e, mv.y - mx);
-            float v2 = fmaf(__uint_as_float(a[4 * q + 2]), p.scale_log2e, mv.z - mx), v3 = fmaf(__uint_as_float(a[4 * q + 3]), p.scale_log2e, mv.w - mx);
-            if (p.seq2seq) {
-              const int j = c0 + 4 * q;
-              if (j > i && j > p.obj_end) v0 += blocked;
-              if (j + 1 > i && j + 1 > p.obj_end) v1 += blocked;
-              if (j + 2 > i && j + 2 > p.obj_end) v2 += blocked;
-              if (j + 3 > i && j + 3 > p.obj_end) v3 += blocked;
-            }
-            const float e0 = at_ex2(v0), e1 = at_ex2(v1), e2 = at_ex2(v2), e3 = at_ex2(v3);
-            sum0 += e0 + e2; sum1 += e1 + e3;
-            pk[2 * q] = pack_bf16x2(e0, e1);
-            pk[2 * q + 1] = pack_bf16x2(e2, e3);
+          for (int c = 0; c < 32; c += 2) {
+            const float e0 = at_ex2(fmaf(v[c], AT_LOG2E, nmx)), e1 = at_ex2(fmaf(v[c + 1], AT_LOG2E, nmx));
+            sum0 += e0; sum1 += e1;
+            pk[c >> 1] = pack_bf16x2(e0, e1);
           }
           tmem_st_32x16(tl + (c0 >> 1), pk);
         } else {
           uint32_t a[16], pk[8];
+          float v[16];
           tmem_ld_32x16(tl + c0, a);
           tmem_ld_wait();
+          jt_scores<16>(a, v, mrow, p.scale, s2s, c0, i, p.obj_end);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 mv = *reinterpret_cast<const float4*>(mrow + c0 + 4 * q);
-            float v0 = fmaf(__uint_as_float(a[4 * q]), p.scale_log2e, mv.x - mx), v1 = fmaf(__uint_as_float(a[4 * q + 1]), p.scale_log2e, mv.y - mx);
-            float v2 = fmaf(__uint_as_float(a[4 * q + 2]), p.scale_log2e, mv.z - mx), v3 = fmaf(__uint_as_float(a[4 * q + 3]), p.scale_log2e, mv.w - mx);
-            if (p.seq2seq) {
-              const int j = c0 + 4 * q;
-              if (j > i && j > p.obj_end) v0 += blocked;
-              if (j + 1 > i && j + 1 > p.obj_end) v1 += blocked;
-              if (j + 2 > i && j + 2 > p.obj_end) v2 += blocked;
-              if (j + 3 > i && j + 3 > p.obj_end) v3 += blocked;
-            }
-            const float e0 = at_ex2(v0), e1 = at_ex2(v1), e2 = at_ex2(v2), e3 = at_ex2(v3);
-            sum0 += e0 + e2; sum1 += e1 + e3;
-            pk[2 * q] = pack_bf16x2(e0, e1);
-            pk[2 * q + 1] = pack_bf16x2(e2, e3);
+          for (int c = 0; c < 16; c += 2) {
+            const float e0 = at_ex2(fmaf(v[c], AT_LOG2E, nmx)), e1 = at_ex2(fmaf(v[c + 1], AT_LOG2E, nmx));
+            sum0 += e0; sum1 += e1;
+            pk[c >> 1] = pack_bf16x2(e0, e1);
           }
           tmem_st_32x8(tl + (c0 >> 1), pk);
         }
@@ -566,9 +630,11 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[slot]);
       const float inv = 1.0f / (sum0 + sum1);
+      if (quarter == 0) JT_STAMP(n, 8);
 
       mbar_wait(&o_full[slot], u & 1);
       tc_fence_after();
+      if (quarter == 0) JT_STAMP(n, 9);
       uint32_t o0[32], o1[32];
       tmem_ld_32x32(tl + 192, o0);
       tmem_ld_32x32(tl + 224, o1);
@@ -576,26 +642,39 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[slot]);
-      if (valid) {
-        uint4* dst = reinterpret_cast<uint4*>(p.out + (long long)g * C + head * 64);
+      // the warp's 32 x 64 output tile goes through shared memory (TMA swizzle pattern, conflict-free 16-byte stores) and
+      // leaves as ONE tensor store: 32 full 128-byte rows instead of 256 scattered 16-byte pieces; rows past R are clipped
+      if (lane == 0) bulk_wait_read<0>();             // the previous tile's store has finished reading the staging buffer
+      __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          dst[q] = make_uint4(pack_bf16x2(__uint_as_float(o0[8 * q]) * inv, __uint_as_float(o0[8 * q + 1]) * inv),
-                              pack_bf16x2(__uint_as_float(o0[8 * q + 2]) * inv, __uint_as_float(o0[8 * q + 3]) * inv),
-                              pack_bf16x2(__uint_as_float(o0[8 * q + 4]) * inv, __uint_as_float(o0[8 * q + 5]) * inv),
-                              pack_bf16x2(__uint_as_float(o0[8 * q + 6]) * inv, __uint_as_float(o0[8 * q + 7]) * inv));
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(stg + stg_row + (((uint32_t)q ^ stg_swz) << 4)) =
+            make_uint4(pack_bf16x2(__uint_as_float(o0[8 * q]) * inv, __uint_as_float(o0[8 * q + 1]) * inv),
+                       pack_bf16x2(__uint_as_float(o0[8 * q + 2]) * inv, __uint_as_float(o0[8 * q + 3]) * inv),
+                       pack_bf16x2(__uint_as_float(o0[8 * q + 4]) * inv, __uint_as_float(o0[8 * q + 5]) * inv),
+                       pack_bf16x2(__uint_as_float(o0[8 * q + 6]) * inv, __uint_as_float(o0[8 * q + 7]) * inv));
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          dst[4 + q] = make_uint4(pack_bf16x2(__uint_as_float(o1[8 * q]) * inv, __uint_as_float(o1[8 * q + 1]) * inv),
-                                  pack_bf16x2(__uint_as_float(o1[8 * q + 2]) * inv, __uint_as_float(o1[8 * q + 3]) * inv),
-                                  pack_bf16x2(__uint_as_float(o1[8 * q + 4]) * inv, __uint_as_float(o1[8 * q + 5]) * inv),
-                                  pack_bf16x2(__uint_as_float(o1[8 * q + 6]) * inv, __uint_as_float(o1[8 * q + 7]) * inv));
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(stg + stg_row + (((uint32_t)(4 + q) ^ stg_swz) << 4)) =
+            make_uint4(pack_bf16x2(__uint_as_float(o1[8 * q]) * inv, __uint_as_float(o1[8 * q + 1]) * inv),
+                       pack_bf16x2(__uint_as_float(o1[8 * q + 2]) * inv, __uint_as_float(o1[8 * q + 3]) * inv),
+                       pack_bf16x2(__uint_as_float(o1[8 * q + 4]) * inv, __uint_as_float(o1[8 * q + 5]) * inv),
+                       pack_bf16x2(__uint_as_float(o1[8 * q + 6]) * inv, __uint_as_float(o1[8 * q + 7]) * inv));
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (row0 + quarter * 32 < p.R) tma_store_2d(&tmap_out, stg, head * 64, row0 + quarter * 32);
+        bulk_commit();
       }
+      __syncwarp();
+      if (quarter == 0) JT_STAMP(n, 10);
     }
   }
 
+  if (warp >= JT_SOFTMAX_WARP0 && lane == 0) bulk_wait_all();     // this warp's output stores are globally performed
   tc_fence_before();
   __syncthreads();
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[1] = (unsigned long long)clock64();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -617,17 +696,26 @@ static int launch_joint_tc(const void* qkv, const JointTcParams& p, cudaStream_t
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) != MVLT_OK) return rc;
   if ((rc = make_tmap(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, p.R, 3 * C, 3 * C, 64, SP, CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) != MVLT_OK) return rc;
+  CUtensorMap tout;
+  if ((rc = make_tmap(&tout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.out, p.R, C, C, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_NONE)) != MVLT_OK) return rc;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.n_items < sms ? p.n_items : sms;
-  cudaError_t e = launch_k(joint_attn_tc_kernel<SP, NS>, dim3(grid), dim3(JT_THREADS), (size_t)P::SMEM, stream, tq, tkv, p);
+  cudaError_t e = launch_k(joint_attn_tc_kernel<SP, NS>, dim3(grid), dim3(JT_THREADS), (size_t)P::SMEM, stream, tq, tkv, tout, p);
   return e == cudaSuccess ? MVLT_OK : (int)e;
 }
 
 }  // namespace mvlt
 
 using namespace mvlt;
+
+// debug hook (not part of include/mvlt_b200.h): device buffer of >= 256 u64 stamped by CTA 0 of every later joint-attention launch
+extern "C" int mvlt_debug_attn_trace(void* dev_buf) {
+  g_attn_trace = reinterpret_cast<unsigned long long*>(dev_buf);
+  return MVLT_OK;
+}
 
 // Swin window attention on the tensor cores.  qkv: bf16 [B*nW*49, 3C], rows WINDOW-MAJOR for this block's shift (row
 // (b*nW + w)*49 + i = token i of window w of the rolled image b); out: bf16 [B*H*W, C], natural token order.
@@ -660,6 +748,10 @@ extern "C" int mvlt_window_attention_tc(const void* qkv, void* out, const float*
   if (groups < 1) groups = 1;
   if (groups > p.n_pairs) groups = p.n_pairs;
   p.n_groups = groups;
+  auto log2_exact = [](int v) { int s = 0; while ((1 << s) < v) ++s; return (1 << s) == v ? s : -1; };
+  p.nW_shift = log2_exact(p.nWh * p.nWw);
+  p.nWw_shift = log2_exact(p.nWw);
+  if (p.nW_shift < 0 || p.nWw_shift < 0) p.nW_shift = p.nWw_shift = -1;
   p.scale_log2e = scale * AT_LOG2E;
   CUtensorMap tm;
   if ((rc = make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, n_windows * 49, 3LL * C, 3LL * C, 32, 49, CU_TENSOR_MAP_SWIZZLE_64B,
@@ -682,7 +774,8 @@ extern "C" int mvlt_joint_attention_tc(const void* qkv, void* out, const float* 
   if (rc != MVLT_OK) return rc;
   JointTcParams p;
   p.out = reinterpret_cast<bf16*>(out); p.kmask = kmask; p.R = (int)R; p.S = S; p.B = B; p.heads = heads; p.seq2seq = seq2seq;
-  p.obj_end = obj_end; p.scale_log2e = scale * AT_LOG2E;
+  p.obj_end = obj_end; p.scale = scale;
+  p.trace = g_attn_trace;
   p.n_items = (int)((R + 127) / 128) * heads;
   if (S >= 128 && S <= 144) return launch_joint_tc<144, 2>(qkv, p, stream);
   if (S >= 64 && S <= 96) return launch_joint_tc<96, 3>(qkv, p, stream);

@@ -27,6 +27,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "cg2.cuh"
 #include "tmap.cuh"
 
 namespace mvlt {
@@ -88,59 +89,6 @@ struct GemmParams {
 };
 static unsigned long long* g_gemm_trace = nullptr;
 #define GEMM_STAMP(idx) do { if (p.trace != nullptr && blockIdx.x == 0 && lane == 0) p.trace[(idx)] = (unsigned long long)clock64(); } while (0)
-
-// ---- cta_group::2 PTX ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst)), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish_cg2() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-// mbarrier arrive (on the same barrier of BOTH CTAs of the pair) once all MMAs issued so far by this thread retire
-__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-// TMA tile load into THIS CTA's smem; completion bytes are counted on the LEADER CTA's mbarrier (peer bit cleared)
-__device__ __forceinline__ void tma_load_cg2(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
-      : "memory");
-}
-// im2col-mode TMA load (NHWC activation, rank-4 map {C, W, H, N}): 128 output pixels x 64 channels starting at the pixel
-// whose filter window has its corner at (w, h) in image n, shifted by the filter tap (off_w, off_h); out-of-image taps
-// and pixels beyond the last image arrive as zeros.  Same barrier convention as tma_load_cg2.
-__device__ __forceinline__ void tma_load_im2col_cg2(void* smem_dst, const void* tmap, uint64_t* bar, int c, int w, int h,
-                                                    int n, uint16_t off_w, uint16_t off_h) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
-        "h"(off_h)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the mbarrier at the same smem offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
 
 // ACT: 0 none, 1 erf-GELU, 2 tanh, 3 ReLU, 4 ReLU then erf-GELU.  ACT 3/4 are the ResNet epilogues: applied LAST, after the
 // residual add (torchvision resnet.py Bottleneck.forward: out += identity; out = relu(out)), bf16 outputs only.

@@ -275,6 +275,10 @@ class SwinTransformer(nn.Module):
         # of the tensor rate): 13.87 k vs 14.00 k pairs/s for the step (profiles/r01_ln_linear_fused_experiment.log).
         ln_lin_widths = tuple(int(v) for v in os.environ.get("MVLT_FUSED_LN_LINEAR", "").split(",") if v.strip()) \
             if self.precision == "bf16" else ()
+        # proj + residual + LN2 + fc1 + GELU + fc2 + residual as ONE tcgen05 kernel on CTA pairs (csrc/swin_tail.cu; the new residual
+        # rows stay in tensor memory between the two halves) for the widths in MVLT_BLOCK_TAIL (bf16 mode; default 192,384).
+        tail_widths = tuple(int(v) for v in os.environ.get("MVLT_BLOCK_TAIL", "192,384").split(",") if v.strip()) \
+            if self.precision == "bf16" else ()
         taps = self.taps
         if taps is not None:
             taps["patch_embed"] = X.clone().view(B, -1, X.shape[-1])
@@ -305,6 +309,12 @@ class SwinTransformer(nn.Module):
                 else:
                     o = ops.window_attention(qkv, w["relbias"], B, H, W, C, blk.num_heads, blk.window_size, blk.shift_size,
                                              blk.attn.scale)
+                if C in tail_widths and C in ops.BLOCK_TAIL_WIDTHS and w["fc1_w"].shape[0] == 4 * C:
+                    ops.swin_block_tail(X, o, w["proj_w"], w["proj_b"], w["n2w"], w["n2b"], blk.norm2.eps, w["fc1_w"], w["fc1_b"],
+                                        w["fc2_w"], w["fc2_b"])
+                    if taps is not None and i < 2:
+                        taps[f"s{s}b{i}"] = X.clone().view(B, H * W, C)
+                    continue
                 ops.linear(o, w["proj_w"], w["proj_b"], residual=X, out=X)
                 if C in fused_widths and C in ops.FUSED_MLP_WIDTHS and w["fc1_w"].shape[0] == 4 * C:
                     ops.swin_mlp(X, w["n2w"], w["n2b"], blk.norm2.eps, w["fc1_w"], w["fc1_b"], w["fc2_w"], w["fc2_b"])

@@ -175,6 +175,32 @@ def swin_mlp(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: floa
     return x
 
 
+BLOCK_TAIL_WIDTHS = (192, 384)
+
+
+def swin_block_tail(x: torch.Tensor, o: Optional[torch.Tensor], wproj: Optional[torch.Tensor], bproj: Optional[torch.Tensor],
+                    gamma: torch.Tensor, beta: torch.Tensor, eps: float, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor,
+                    b2: torch.Tensor) -> torch.Tensor:
+    """x += o @ wproj.T + bproj; x += fc2(gelu(fc1(layernorm(x)))) — in place, ONE kernel on CTA pairs (fp32 x [M, C], bf16 o and
+    weights, C in BLOCK_TAIL_WIDTHS).  o=None: the MLP half only."""
+    lib = _lib.ensure_init()
+    M, C, ldx = _rows2d(x)
+    hidden = w1.shape[0]
+    assert x.dtype == torch.float32 and w1.dtype == w2.dtype == torch.bfloat16
+    assert w1.shape == (hidden, C) and w2.shape == (C, hidden) and w1.is_contiguous() and w2.is_contiguous()
+    if o is not None:
+        assert o.dtype == torch.bfloat16 and o.shape == (M, C) and o.is_contiguous()
+        assert wproj.dtype == torch.bfloat16 and wproj.shape == (C, C) and wproj.is_contiguous()
+        assert bproj.dtype == torch.float32 and bproj.is_contiguous() and bproj.numel() == C
+    for t, n in ((gamma, C), (beta, C), (b1, hidden), (b2, C)):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n
+    rc = lib.mvlt_swin_block_tail(_ptr(o), x.data_ptr(), ldx, _ptr(wproj) if o is not None else None,
+                                  _ptr(bproj) if o is not None else None, gamma.data_ptr(), beta.data_ptr(), float(eps),
+                                  w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), M, C, hidden, _stream())
+    _lib.check(rc, f"mvlt_swin_block_tail(M={M},C={C})")
+    return x
+
+
 FUSED_LN_LINEAR_WIDTHS = (192, 384)
 
 

@@ -3,15 +3,15 @@
 A plain-PyTorch (CPU, fp32 or fp64) functional restatement of the reference algorithm, written
 over a flat `state_dict` so it needs neither the reference tree nor HuggingFace module classes
 and can therefore travel to the GPU box.  Only `tests/`, `__graft_entry__.smoke()` and
-`bench.py`'s `cpu_baseline` / `--impl reference` legs may import it; the product package
-(`medical_vision_langauge_transformer_b200`) never does.
+`bench.py`'s baseline legs (`cpu_baseline`, `--impl reference`, the secondary `gpu_eager_baseline`, the `parity` check)
+may import it; the product package (`medical_vision_langauge_transformer_b200`) never does.
 
 Pinning status: the reference ships NO golden vectors or tests for this path (SURVEY.md §4, §8c:
 "parity unpinned" on the reference side).  This restatement is therefore pinned operationally:
-  * `tests/test_oracle_vs_reference.py` runs it against the real, unmodified reference modules
+  * `tests/test_oracle_cpu.py::test_oracle_vs_live_reference` runs it against the real, unmodified reference modules
     (imported through `oracle/ref_shims.py`) whenever `/root/reference` is present, and
   * `oracle/make_golden.py` stores outputs OF THE REAL REFERENCE on seeded inputs/weights under
-    `tests/golden/`; `tests/test_oracle_golden.py` checks this file against them everywhere.
+    `tests/golden/`; the other tests of `tests/test_oracle_cpu.py` check this file against them everywhere.
 
 Every function cites the reference lines it follows.  `vfe.py` = modules/visual_feature_extractor.py,
 `model.py` = modules/model.py (both under the reference root), `HF:` = transformers 5.5.0

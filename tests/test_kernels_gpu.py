@@ -294,6 +294,44 @@ def test_window_attention_tc_batches(cuda, B, H, C, heads, shift):
     assert torch.equal(out, out2), "run-to-run bit reproducibility"
 
 
+def _tail_case(M, C, seed):
+    x = rnd(M, C, seed=seed)
+    o = rnd(M, C, seed=seed + 1).bfloat16()
+    wp, bp = rnd(C, C, seed=seed + 2, scale=C ** -0.5).bfloat16(), rnd(C, seed=seed + 3, scale=0.1)
+    g, b = 1 + rnd(C, seed=seed + 4, scale=0.1), rnd(C, seed=seed + 5, scale=0.1)
+    w1, b1 = rnd(4 * C, C, seed=seed + 6, scale=C ** -0.5).bfloat16(), rnd(4 * C, seed=seed + 7, scale=0.1)
+    w2, b2 = rnd(C, 4 * C, seed=seed + 8, scale=(4 * C) ** -0.5).bfloat16(), rnd(C, seed=seed + 9, scale=0.1)
+    return x, o, wp, bp, g, b, w1, b1, w2, b2
+
+
+@pytest.mark.parametrize("M,C", [(256, 384), (12544, 384), (300, 384), (37, 384), (1568, 192), (50176, 192), (129, 192)])
+@pytest.mark.parametrize("with_proj", [True, False])
+def test_swin_block_tail(cuda, M, C, with_proj):
+    """proj + residual + LayerNorm + fc1 + GELU + fc2 + residual in one CTA-pair kernel against (1) a torch restatement with
+    the kernel's rounding points (bf16 LayerNorm output and hidden activation) and (2) the unfused kernel chain."""
+    from medical_vision_langauge_transformer_b200 import ops
+    x, o, wp, bp, g, b, w1, b1, w2, b2 = _tail_case(M, C, seed=C + M)
+    x1 = x + o.float() @ wp.float().t() + bp if with_proj else x.clone()
+    a = F.layer_norm(x1, (C,), g, b, 1e-5).bfloat16().float()
+    h = F.gelu(a @ w1.float().t() + b1).bfloat16().float()
+    ref = x1 + h @ w2.float().t() + b2
+    # unfused chain on the same kernels the model used before
+    xc = x.clone()
+    if with_proj:
+        ops.linear(o, wp, bp, residual=xc, out=xc)
+    an = ops.layernorm(xc, g, b, 1e-5, torch.bfloat16)
+    hn = ops.linear(an, w1, b1, act=ops.ACT_GELU)
+    ops.linear(hn, w2, b2, residual=xc, out=xc)
+    xf = x.clone()
+    ops.swin_block_tail(xf, o if with_proj else None, wp, bp, g, b, 1e-5, w1, b1, w2, b2)
+    assert torch.isfinite(xf).all()
+    assert relerr(xf, ref) < 3e-3, (M, C, relerr(xf, ref))
+    assert relerr(xf, xc) < 3e-3, (M, C, relerr(xf, xc))
+    xf2 = x.clone()
+    ops.swin_block_tail(xf2, o if with_proj else None, wp, bp, g, b, 1e-5, w1, b1, w2, b2)
+    assert torch.equal(xf, xf2), "run-to-run bit reproducibility"
+
+
 @pytest.mark.parametrize("B,H,C,shift", [(2, 56, 96, 0), (2, 56, 96, 3), (3, 28, 192, 3), (2, 14, 384, 3), (5, 7, 768, 0)])
 def test_layernorm_winmajor(cuda, B, H, C, shift):
     from medical_vision_langauge_transformer_b200 import ops
