@@ -316,8 +316,9 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const WinTcP
 // BERT joint attention (head_dim 64)
 // =====================================================================================================================
 constexpr int JT_SLOTS = 2;
-constexpr int JT_SOFTMAX_WARP0 = 3;              // warp 0: Q / K producer, warp 1: MMA issuer, warp 2: V producer
-constexpr int JT_THREADS = (JT_SOFTMAX_WARP0 + 4 * JT_SLOTS) * 32;
+constexpr int JT_SOFTMAX_WARP0 = 3;              // warp 0: Q / K producer, warp 1: MMA issuer, warp 2: V producer + key masks
+constexpr int JT_WG_WARPS = 8;                   // softmax warps per slot: TWO threads per score row (each takes half of the keys)
+constexpr int JT_THREADS = (JT_SOFTMAX_WARP0 + JT_WG_WARPS * JT_SLOTS) * 32;
 constexpr int JT_Q_BYTES = 128 * 128;
 
 template <int SP, int NS> struct JtPlan {
@@ -325,8 +326,11 @@ template <int SP, int NS> struct JtPlan {
   static constexpr int QK_BYTES = JT_Q_BYTES + NS * KV_BYTES;     // released as soon as Q.K^T has retired
   static constexpr int V_BYTES = NS * KV_BYTES;                   // released when P.V has retired
   static constexpr int MASK_FLOATS = JT_SLOTS * NS * SP;
-  static constexpr int STAGING_BYTES = 4 * JT_SLOTS * 4096;       // one [32 rows x 128 B] output tile per softmax warp
-  static constexpr int SMEM = JT_SLOTS * (QK_BYTES + V_BYTES) + STAGING_BYTES + MASK_FLOATS * 4 + 9 * JT_SLOTS * 8 + 16 + 1024;
+  static constexpr int STAGING_BYTES = JT_WG_WARPS * JT_SLOTS * 2048;   // one [32 rows x 64 B] output tile per softmax warp
+  static constexpr int XCH_FLOATS = JT_SLOTS * 2 * 256;           // per slot: partial row maxima [128][2], partial row sums [128][2]
+  static constexpr int KSPLIT = SP == 144 ? 80 : 48;              // keys [0, KSPLIT) -> thread half 0, [KSPLIT, SP) -> half 1
+  static constexpr int SMEM = JT_SLOTS * (QK_BYTES + V_BYTES) + STAGING_BYTES + (MASK_FLOATS + XCH_FLOATS) * 4 + 9 * JT_SLOTS * 8 + 16 + 1024;
+  static_assert(KSPLIT % 16 == 0 && (SP - KSPLIT) % 16 == 0, "each half is a whole number of 16-column TMEM loads");
   static_assert(KV_BYTES % 1024 == 0 && SP % 16 == 0 && SP <= 144, "K / V buffers are whole SWIZZLE_128B atoms; S columns + O fit 256");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -384,7 +388,8 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint8_t* smem_v = smem + JT_SLOTS * QKB;
   uint8_t* staging = smem_v + JT_SLOTS * VB;       // 1024-byte aligned: QKB and VB are multiples of 1024
   float* mask_s = reinterpret_cast<float*>(staging + P::STAGING_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(mask_s + P::MASK_FLOATS);
+  float* xch = mask_s + P::MASK_FLOATS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + P::XCH_FLOATS);
   uint64_t* qk_full = bars;                      // TMA (Q, K) -> MMA
   uint64_t* qk_empty = bars + JT_SLOTS;          // Q.K^T retired -> Q / K producer
   uint64_t* v_full = bars + 2 * JT_SLOTS;        // TMA (V) -> MMA
@@ -406,7 +411,7 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tma_prefetch_desc(&tmap_out);
     for (int s = 0; s < JT_SLOTS; ++s) {
       mbar_init(&qk_full[s], 1); mbar_init(&qk_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4); mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 4);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], JT_WG_WARPS); mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], JT_WG_WARPS);
       mbar_init(&m_full[s], 32);                  // every lane of the V-producer warp: cp.async.mbarrier.arrive.noinc
     }
     mbar_fence_init();
@@ -542,15 +547,26 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       else if (clock64() - t_last > AT_WATCHDOG) __trap();
     }
   } else {
-    // ------------------------------- softmax + epilogue ---------------------------------------------------------------
-    const int slot = (warp - JT_SOFTMAX_WARP0) >> 2;
+    // ------------------------------- softmax + epilogue: TWO threads per score row -------------------------------------
+    // Warps 3 + 8 slot .. : the two warps that own the same TMEM lane quarter split the keys (thread half 0: keys [0, KSPLIT),
+    // half 1: the rest) — half the dependent chain per thread and twice the warps to hide tcgen05.ld / MUFU latency.  Partial row
+    // maxima and sums are exchanged through shared memory around two named barriers of the slot's 256 threads; the second
+    // one also separates every read of the score columns from the P stores that alias them.
+    constexpr int KSPLIT = P::KSPLIT;
+    const int wsub = (warp - JT_SOFTMAX_WARP0) % JT_WG_WARPS;
+    const int slot = (warp - JT_SOFTMAX_WARP0) / JT_WG_WARPS;
     const int quarter = warp & 3;
+    const int half = wsub >> 2;                      // warps 3..6 -> quarters 3,0,1,2 (half 0), warps 7..10 -> the same quarters (half 1)
     const int r = quarter * 32 + lane;
     const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 256;
     float* msk = mask_s + slot * NS * SP;
-    uint8_t* stg = staging + (warp - JT_SOFTMAX_WARP0) * 4096;     // this warp's output tile: 32 rows x 128 B, SWIZZLE_128B
-    const uint32_t stg_row = (uint32_t)lane * 128u, stg_swz = (uint32_t)lane & 7u;
+    float* x_max = xch + slot * 512;                 // [128][2]
+    float* x_sum = x_max + 256;                      // [128][2]
+    uint8_t* stg = staging + (warp - JT_SOFTMAX_WARP0) * 2048;     // this warp's output tile: 32 rows x 64 B, SWIZZLE_64B
+    const uint32_t stg_row = (uint32_t)lane * 64u, stg_swz = ((uint32_t)lane >> 1) & 3u;
     const bool s2s = p.seq2seq != 0;
+    const int k_lo = half ? KSPLIT : 0;              // this thread's keys [k_lo, k_lo + NK)
+    constexpr int NK0 = KSPLIT, NK1 = SP - KSPLIT;
     for (int n = slot, u = 0; n < my_tiles; n += JT_SLOTS, ++u) {
       int row0, head, b0, ns;
       item_of(n, row0, head, b0, ns);
@@ -560,90 +576,81 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const int i = g - b * p.S;                         // position of this row in its sample
       const float* mrow = msk + (b - b0) * SP;
       mbar_wait(&m_full[slot], u & 1);
-      if (quarter == 0) JT_STAMP(n, 5);
+      if (wsub == 1) JT_STAMP(n, 5);
 
       mbar_wait(&s_full[slot], u & 1);
       tc_fence_after();
-      if (quarter == 0) JT_STAMP(n, 6);
-      // pass 1: row maximum
+      if (wsub == 1) JT_STAMP(n, 6);
+      // pass 1: maximum over this thread's keys, 16 columns per TMEM load
       float mx = AT_NEG_BIG;
+      const int nk = half ? NK1 : NK0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < nk; c0 += 16) {
+        uint32_t a[16];
+        float v[16];
+        tmem_ld_32x16(tl + k_lo + c0, a);
+        tmem_ld_wait();
+        jt_scores<16>(a, v, mrow, p.scale, s2s, k_lo + c0, i, p.obj_end);
+        float m0 = fmaxf(v[0], v[1]), m1 = fmaxf(v[2], v[3]), m2 = fmaxf(v[4], v[5]), m3 = fmaxf(v[6], v[7]);
 #pragma unroll
-      for (int c0 = 0; c0 < SP; c0 += 32) {
-        if (SP - c0 >= 32) {
-          uint32_t a[32];
-          float v[32];
-          tmem_ld_32x32(tl + c0, a);
-          tmem_ld_wait();
-          jt_scores<32>(a, v, mrow, p.scale, s2s, c0, i, p.obj_end);
-          float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
-#pragma unroll
-          for (int c = 4; c < 32; c += 4) { m0 = fmaxf(m0, v[c]); m1 = fmaxf(m1, v[c + 1]); m2 = fmaxf(m2, v[c + 2]); m3 = fmaxf(m3, v[c + 3]); }
-          mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-        } else {
-          uint32_t a[16];
-          float v[16];
-          tmem_ld_32x16(tl + c0, a);
-          tmem_ld_wait();
-          jt_scores<16>(a, v, mrow, p.scale, s2s, c0, i, p.obj_end);
-          float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
-#pragma unroll
-          for (int c = 4; c < 16; c += 4) { m0 = fmaxf(m0, v[c]); m1 = fmaxf(m1, v[c + 1]); m2 = fmaxf(m2, v[c + 2]); m3 = fmaxf(m3, v[c + 3]); }
-          mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-        }
+        for (int c = 8; c < 16; c += 4) { m0 = fmaxf(m0, v[c]); m1 = fmaxf(m1, v[c + 1]); m2 = fmaxf(m2, v[c + 2]); m3 = fmaxf(m3, v[c + 3]); }
+        mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
       }
-      if (quarter == 0) JT_STAMP(n, 7);
-      // pass 2: exp2((v - max) * log2e), row sum, P as bf16 pairs over the score columns already consumed (columns c0/2..)
+      x_max[r * 2 + half] = mx;
+      named_bar_sync(1 + slot, JT_WG_WARPS * 32);
+      mx = fmaxf(mx, x_max[r * 2 + (half ^ 1)]);
+      if (wsub == 1) JT_STAMP(n, 7);
+      // pass 2: exp2((v - max) * log2e), partial row sum; P as bf16 pairs, held in registers until every thread of the slot
+      // has finished reading the score columns
       const float nmx = -mx * AT_LOG2E;
       float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pk[NK0 / 2];
 #pragma unroll
-      for (int c0 = 0; c0 < SP; c0 += 32) {
-        if (SP - c0 >= 32) {
-          uint32_t a[32], pk[16];
-          float v[32];
-          tmem_ld_32x32(tl + c0, a);
-          tmem_ld_wait();
-          jt_scores<32>(a, v, mrow, p.scale, s2s, c0, i, p.obj_end);
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            const float e0 = at_ex2(fmaf(v[c], AT_LOG2E, nmx)), e1 = at_ex2(fmaf(v[c + 1], AT_LOG2E, nmx));
-            sum0 += e0; sum1 += e1;
-            pk[c >> 1] = pack_bf16x2(e0, e1);
-          }
-          tmem_st_32x16(tl + (c0 >> 1), pk);
-        } else {
-          uint32_t a[16], pk[8];
+      for (int cc = 0; cc < NK0 / 16; ++cc) {
+        if (cc * 16 < nk) {       // warp-uniform
+          uint32_t a[16];
           float v[16];
-          tmem_ld_32x16(tl + c0, a);
+          tmem_ld_32x16(tl + k_lo + cc * 16, a);
           tmem_ld_wait();
-          jt_scores<16>(a, v, mrow, p.scale, s2s, c0, i, p.obj_end);
+          jt_scores<16>(a, v, mrow, p.scale, s2s, k_lo + cc * 16, i, p.obj_end);
 #pragma unroll
           for (int c = 0; c < 16; c += 2) {
             const float e0 = at_ex2(fmaf(v[c], AT_LOG2E, nmx)), e1 = at_ex2(fmaf(v[c + 1], AT_LOG2E, nmx));
             sum0 += e0; sum1 += e1;
-            pk[c >> 1] = pack_bf16x2(e0, e1);
+            pk[cc * 8 + (c >> 1)] = pack_bf16x2(e0, e1);
           }
-          tmem_st_32x8(tl + (c0 >> 1), pk);
+        }
+      }
+      x_sum[r * 2 + half] = sum0 + sum1;
+      named_bar_sync(1 + slot, JT_WG_WARPS * 32);
+      // P columns: key pair (2q, 2q + 1) -> TMEM column q of the slot (aliasing the score columns, now dead)
+#pragma unroll
+      for (int cc = 0; cc < NK0 / 16; ++cc) {
+        if (cc * 16 < nk) {
+          uint32_t t8[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) t8[q] = pk[cc * 8 + q];
+          tmem_st_32x8(tl + ((k_lo + cc * 16) >> 1), t8);
         }
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[slot]);
-      const float inv = 1.0f / (sum0 + sum1);
-      if (quarter == 0) JT_STAMP(n, 8);
+      const float inv = 1.0f / ((sum0 + sum1) + x_sum[r * 2 + (half ^ 1)]);
+      if (wsub == 1) JT_STAMP(n, 8);
 
       mbar_wait(&o_full[slot], u & 1);
       tc_fence_after();
-      if (quarter == 0) JT_STAMP(n, 9);
-      uint32_t o0[32], o1[32];
-      tmem_ld_32x32(tl + 192, o0);
-      tmem_ld_32x32(tl + 224, o1);
+      if (wsub == 1) JT_STAMP(n, 9);
+      uint32_t o0[32];
+      tmem_ld_32x32(tl + 192 + half * 32, o0);          // this thread's 32 of the row's 64 output columns
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[slot]);
-      // the warp's 32 x 64 output tile goes through shared memory (TMA swizzle pattern, conflict-free 16-byte stores) and
-      // leaves as ONE tensor store: 32 full 128-byte rows instead of 256 scattered 16-byte pieces; rows past R are clipped
+      // the warp's 32 x 32 output tile goes through shared memory (TMA swizzle pattern, conflict-free 16-byte stores) and
+      // leaves as ONE tensor store of 32 rows x 64 bytes; rows past R are clipped
       if (lane == 0) bulk_wait_read<0>();             // the previous tile's store has finished reading the staging buffer
       __syncwarp();
 #pragma unroll
@@ -653,21 +660,14 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                        pack_bf16x2(__uint_as_float(o0[8 * q + 2]) * inv, __uint_as_float(o0[8 * q + 3]) * inv),
                        pack_bf16x2(__uint_as_float(o0[8 * q + 4]) * inv, __uint_as_float(o0[8 * q + 5]) * inv),
                        pack_bf16x2(__uint_as_float(o0[8 * q + 6]) * inv, __uint_as_float(o0[8 * q + 7]) * inv));
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<uint4*>(stg + stg_row + (((uint32_t)(4 + q) ^ stg_swz) << 4)) =
-            make_uint4(pack_bf16x2(__uint_as_float(o1[8 * q]) * inv, __uint_as_float(o1[8 * q + 1]) * inv),
-                       pack_bf16x2(__uint_as_float(o1[8 * q + 2]) * inv, __uint_as_float(o1[8 * q + 3]) * inv),
-                       pack_bf16x2(__uint_as_float(o1[8 * q + 4]) * inv, __uint_as_float(o1[8 * q + 5]) * inv),
-                       pack_bf16x2(__uint_as_float(o1[8 * q + 6]) * inv, __uint_as_float(o1[8 * q + 7]) * inv));
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        if (row0 + quarter * 32 < p.R) tma_store_2d(&tmap_out, stg, head * 64, row0 + quarter * 32);
+        if (row0 + quarter * 32 < p.R) tma_store_2d(&tmap_out, stg, head * 64 + half * 32, row0 + quarter * 32);
         bulk_commit();
       }
       __syncwarp();
-      if (quarter == 0) JT_STAMP(n, 10);
+      if (wsub == 1) JT_STAMP(n, 10);
     }
   }
 
@@ -697,7 +697,7 @@ static int launch_joint_tc(const void* qkv, const JointTcParams& p, cudaStream_t
   if ((rc = make_tmap(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, p.R, 3 * C, 3 * C, 64, SP, CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) != MVLT_OK) return rc;
   CUtensorMap tout;
-  if ((rc = make_tmap(&tout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.out, p.R, C, C, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B,
+  if ((rc = make_tmap(&tout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.out, p.R, C, C, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B,
                       CU_TENSOR_MAP_L2_PROMOTION_NONE)) != MVLT_OK) return rc;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

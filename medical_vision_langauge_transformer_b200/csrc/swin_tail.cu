@@ -34,26 +34,37 @@ namespace mvlt {
 constexpr int BT_THREADS = 18 * 32;        // warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-17 compute
 constexpr int BT_CW0 = 2;                  // first compute warp
 constexpr int BT_NCW = 16;
-constexpr int BT_SLOT = 96 * 128;          // weight ring slot: a [<= 96 rows, 64 k] bf16 tile
 constexpr int BT_ACC1_COL = 384;
 
+// Shared-memory plan.  What the first version's clock64 trace showed (profiles/r02_tail_trace_v1.log): (1) the residual chunks
+// were only requested after the proj product had retired (their buffers aliased the o tile): 8.7k cycles of exposed HBM time;
+// (2) a 5-slot weight ring (60 KB) behind ~1.5k cycles of L2 latency streamed 23 B/clk where the MMAs want 32: the main loop
+// ran 4.2k cycles per hidden chunk against 3.1k of tensor time; (3) LayerNorm / bias parameters fetched from global memory
+// inside the passes.  Hence: x goes into TENSOR MEMORY first (the proj product then accumulates onto it) through a 3-buffer
+// ring that lives where the hidden activation will (loads start at kernel entry, in parallel with the o tile); all weight
+// tiles are [64 rows, 64 k] (8 KB; C-wide outputs as 128-column sub-tiles) in a deeper ring; A2 is three 16 KB half-chunk
+// buffers instead of two 32 KB chunks; gamma / beta / biases are staged in shared memory.
 template <int C> struct TailPlan {
   static_assert(C == 384 || C == 192, "Swin-S stage 1 / stage 2 widths");
   static constexpr int KB1 = C / 64;                    // k-blocks of the C-wide contractions (proj, fc1)
-  static constexpr int NH = C / 192;                    // 192-column halves of the C-wide outputs (proj, fc2)
+  static constexpr int WN = C == 384 ? 128 : 192;       // output columns per MMA of the C-wide products (proj, fc2)
+  static constexpr int NSUB = C / WN;                   // such sub-tiles per k-block
+  static constexpr int WROWS = WN / 2;                  // weight rows per CTA and tile
+  static constexpr int SLOT = WROWS * 128;              // ring slot bytes (fc1 tiles: 64 rows = 8 KB, fit either way)
   static constexpr int HID = 4 * C;
   static constexpr int NCHUNK = HID / 128;
   static constexpr int XCH = C / 32;                    // 32-column fp32 chunks of a residual row
-  static constexpr int A1_BYTES = KB1 * 16384;          // [128 rows][C] bf16 as KB1 k-blocks of [128][64]; also: o tile, x chunk ring
-  static constexpr int XB = KB1;                        // x chunk buffers (16 KB each) inside the A1 region
-  static constexpr int A2_BYTES = 2 * 16384;            // one [128][128] bf16 hidden chunk; two buffers; also: output staging
-  static constexpr int NSLOT = C == 384 ? 5 : 8;
-  static constexpr int STAT_BYTES = 2 * 128 * 4 * 4;    // per-row partial sums of the four column parts, two passes
-  static constexpr int NUM_BARS = 2 * NSLOT + 12 + XCH + XB;
+  static constexpr int A1_BYTES = KB1 * 16384;          // [128 rows][C] bf16 as KB1 k-blocks of [128][64]; first: the o tile
+  static constexpr int A2_BYTES = 3 * 16384;            // three [128][64] bf16 half-chunk buffers; first: x chunk ring; last: staging
+  static constexpr int NSLOT = C == 384 ? 8 : 8;
+  static constexpr int PAR_BYTES = 2 * C * 4;           // gamma | beta
+  static constexpr int STAT_BYTES = 2 * 128 * 4 * 4;    // per-row partial sums of the four column parts (two passes); b_proj / b2 in turn
+  static constexpr int NUM_BARS = 2 * NSLOT + 16 + XCH + 3;
   static constexpr int AUX_BYTES = 768;
-  static constexpr int SMEM = A1_BYTES + 2 * A2_BYTES + NSLOT * BT_SLOT + STAT_BYTES + AUX_BYTES + 1024;
+  static constexpr int SMEM = A1_BYTES + A2_BYTES + NSLOT * SLOT + PAR_BYTES + STAT_BYTES + AUX_BYTES + 1024;
   static_assert(NUM_BARS * 8 + 8 <= AUX_BYTES, "barrier block");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  static_assert(C * 4 <= 2048, "b_proj / b2 fit one half of the statistics block");
 };
 
 struct TailParams {
@@ -73,30 +84,32 @@ static unsigned long long* g_tail_trace = nullptr;
 template <int C>
 __global__ void __launch_bounds__(BT_THREADS, 1)
 swin_tail_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_x,
-                 const __grid_constant__ CUtensorMap tmap_xs, const __grid_constant__ CUtensorMap tmap_w96, const __grid_constant__ CUtensorMap tmap_w2,
+                 const __grid_constant__ CUtensorMap tmap_xs, const __grid_constant__ CUtensorMap tmap_wp, const __grid_constant__ CUtensorMap tmap_w2,
                  const __grid_constant__ CUtensorMap tmap_w1, const TailParams p) {
   using P = TailPlan<C>;
-  constexpr int KB1 = P::KB1, NH = P::NH, NCHUNK = P::NCHUNK, XCH = P::XCH, XB = P::XB, NSLOT = P::NSLOT;
+  constexpr int KB1 = P::KB1, NSUB = P::NSUB, WN = P::WN, WROWS = P::WROWS, SLOT = P::SLOT, NCHUNK = P::NCHUNK, XCH = P::XCH, NSLOT = P::NSLOT;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* a1 = smem;
   uint8_t* a2 = a1 + P::A1_BYTES;
-  uint8_t* ring = a2 + 2 * P::A2_BYTES;
-  float* stats = reinterpret_cast<float*>(ring + NSLOT * BT_SLOT);
+  uint8_t* ring = a2 + P::A2_BYTES;
+  float* par = reinterpret_cast<float*>(ring + NSLOT * SLOT);         // gamma[C] | beta[C]
+  float* stats = par + 2 * C;                                         // [128][4] sums | [128][4] squares (b_proj first, b2 last)
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats) + P::STAT_BYTES);
   uint64_t* w_full = bars;                    // [NSLOT] TMA -> MMA            (leader CTA's copy counts both CTAs' bytes)
   uint64_t* w_empty = w_full + NSLOT;         // [NSLOT] MMA -> TMA            (multicast commit: one copy per CTA)
   uint64_t* a0_full = w_empty + NSLOT;        // o tile landed                  (leader)
-  uint64_t* acc0_full = a0_full + 1;          // MMA0 retired                   (multicast)
-  uint64_t* a1_full = acc0_full + 1;          // LayerNorm rows written         (leader, 2 x 16 warp arrivals)
+  uint64_t* x_done = a0_full + 1;             // residual rows stored in TMEM   (leader, 2 x 16 warp arrivals)
+  uint64_t* acc0_full = x_done + 1;           // MMA0 retired                   (multicast)
+  uint64_t* a1_full = acc0_full + 1;          // LayerNorm rows written         (leader, 32 arrivals)
   uint64_t* acc1_full = a1_full + 1;          // MMA1(j) retired                (multicast)
   uint64_t* acc1_empty = acc1_full + 1;       // GELU warps have loaded ACC1    (leader, 32 arrivals)
-  uint64_t* a2_full = acc1_empty + 1;         // [2] hidden chunk written       (leader, 32 arrivals)
-  uint64_t* a2_empty = a2_full + 2;           // [2] MMA2 retired               (multicast)
-  uint64_t* acc2_full = a2_empty + 2;         // last MMA2 retired              (multicast)
+  uint64_t* a2_full = acc1_empty + 1;         // [3] hidden half-chunk written  (leader, 2 x 8 warp arrivals)
+  uint64_t* a2_empty = a2_full + 3;           // [3] its MMA2 k-block retired   (multicast)
+  uint64_t* acc2_full = a2_empty + 3;         // last MMA2 retired              (multicast)
   uint64_t* x_full = acc2_full + 1;           // [XCH] residual chunk landed    (local)
-  uint64_t* x_free = x_full + XCH;            // [XB]  chunk buffer consumed    (local, 4 warp arrivals)
+  uint64_t* x_free = x_full + XCH;            // [3]   chunk buffer consumed    (local, 4 warp arrivals)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + P::NUM_BARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -106,20 +119,26 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_consta
   const bool with_proj = p.with_proj != 0;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_o); tma_prefetch_desc(&tmap_x); tma_prefetch_desc(&tmap_xs); tma_prefetch_desc(&tmap_w96); tma_prefetch_desc(&tmap_w2);
+    tma_prefetch_desc(&tmap_o); tma_prefetch_desc(&tmap_x); tma_prefetch_desc(&tmap_xs); tma_prefetch_desc(&tmap_wp); tma_prefetch_desc(&tmap_w2);
     tma_prefetch_desc(&tmap_w1);
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    mbar_init(a0_full, 1); mbar_init(acc0_full, 1); mbar_init(a1_full, 2 * BT_NCW);
+    mbar_init(a0_full, 1); mbar_init(x_done, 2 * BT_NCW); mbar_init(acc0_full, 1); mbar_init(a1_full, 2 * BT_NCW);
     mbar_init(acc1_full, 1); mbar_init(acc1_empty, 2 * BT_NCW);
-    for (int b = 0; b < 2; ++b) { mbar_init(&a2_full[b], 2 * BT_NCW); mbar_init(&a2_empty[b], 1); }
+    for (int b = 0; b < 3; ++b) { mbar_init(&a2_full[b], BT_NCW); mbar_init(&a2_empty[b], 1); mbar_init(&x_free[b], 4); }
     mbar_init(acc2_full, 1);
     for (int c = 0; c < XCH; ++c) mbar_init(&x_full[c], 1);
-    for (int c = 0; c < XB; ++c) mbar_init(&x_free[c], 4);
     mbar_fence_init();
   }
   if (warp == 1) {
     tmem_alloc_cg2(tmem_ptr, 512);
     tmem_relinquish_cg2();
+  }
+  if (warp >= BT_CW0) {      // parameters (static): gamma | beta, and b_proj into the (not yet used) squares half of the statistics block
+    for (int i = threadIdx.x - 64; i < C; i += BT_NCW * 32) {
+      par[i] = __ldg(p.gamma + i);
+      par[C + i] = __ldg(p.beta + i);
+      stats[512 + i] = with_proj ? __ldg(p.b_proj + i) : 0.f;
+    }
   }
   tc_fence_before();
   cluster_sync_all();
@@ -134,42 +153,40 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_consta
       mbar_wait(&w_empty[s], ph ^ 1);
       if (elect_one()) {
         if (rank == 0) mbar_arrive_expect_tx(&w_full[s], 2 * bytes);
-        tma_load_cg2(ring + s * BT_SLOT, tm, &w_full[s], col, row);
+        tma_load_cg2(ring + s * SLOT, tm, &w_full[s], col, row);
       }
       __syncwarp();
       ++cnt;
     };
-    // weights are parameters: the first tiles stream in while the previous kernel drains; o and x wait for it
+    auto load_wp = [&](int kb) { for (int h = 0; h < NSUB; ++h) load_w(&tmap_wp, WROWS * 128, kb * 64, h * WN + (int)rank * WROWS); };
+    auto load_w1 = [&](int j) { for (int kb = 0; kb < KB1; ++kb) load_w(&tmap_w1, 64 * 128, kb * 64, j * 128 + (int)rank * 64); };
+    auto load_w2 = [&](int j) {
+      for (int kb = 0; kb < 2; ++kb)
+        for (int h = 0; h < NSUB; ++h) load_w(&tmap_w2, WROWS * 128, j * 128 + kb * 64, h * WN + (int)rank * WROWS);
+    };
+    // weights are parameters: the ring fills while the previous kernel drains; o and x wait for it
+    int kb_w = 0;
+    if (with_proj)
+      for (; kb_w < KB1 && (kb_w + 1) * NSUB <= NSLOT; ++kb_w) load_wp(kb_w);
+    pdl_grid_sync();
     if (with_proj) {
-      int kb_w = 0;
-      // fill the ring with the first proj tiles before the dependency wait
-      for (; kb_w < KB1 && (kb_w + 1) * NH <= NSLOT; ++kb_w)
-        for (int h = 0; h < NH; ++h) load_w(&tmap_w96, 96 * 128, kb_w * 64, h * 192 + (int)rank * 96);
-      pdl_grid_sync();
       if (elect_one()) {
         if (rank == 0) mbar_arrive_expect_tx(a0_full, 2 * P::A1_BYTES);
         for (int kb = 0; kb < KB1; ++kb) tma_load_cg2(a1 + kb * 16384, &tmap_o, a0_full, kb * 64, row0);
       }
       __syncwarp();
-      for (; kb_w < KB1; ++kb_w)
-        for (int h = 0; h < NH; ++h) load_w(&tmap_w96, 96 * 128, kb_w * 64, h * 192 + (int)rank * 96);
-      mbar_wait(acc0_full, 0);          // MMA0 has consumed the o tile: its buffers now stage the residual chunks
-    } else {
-      pdl_grid_sync();
     }
+    // residual chunks [128 rows, 32 fp32] through the three buffers of the (still unused) A2 region
     for (int c = 0; c < XCH; ++c) {
-      if (c >= XB) mbar_wait(&x_free[c - XB], 0);
+      if (c >= 3) mbar_wait(&x_free[c % 3], ((c / 3) - 1) & 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&x_full[c], 16384);
-        tma_load_2d(a1 + (c % XB) * 16384, &tmap_x, &x_full[c], c * 32, row0);
+        tma_load_2d(a2 + (c % 3) * 16384, &tmap_x, &x_full[c], c * 32, row0);
       }
       __syncwarp();
     }
-    auto load_w1 = [&](int j) { for (int kb = 0; kb < KB1; ++kb) load_w(&tmap_w1, 64 * 128, kb * 64, j * 128 + (int)rank * 64); };
-    auto load_w2 = [&](int j) {
-      for (int kb = 0; kb < 2; ++kb)
-        for (int h = 0; h < NH; ++h) load_w(&tmap_w2, 96 * 128, j * 128 + kb * 64, h * 192 + (int)rank * 96);
-    };
+    if (with_proj)
+      for (; kb_w < KB1; ++kb_w) load_wp(kb_w);
     load_w1(0);
     for (int j = 0; j < NCHUNK; ++j) {
       if (j + 1 < NCHUNK) load_w1(j + 1);
@@ -179,7 +196,7 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_consta
     // ------------------------------- MMA issuer (leader CTA) ----------------------------------------------------------
     pdl_grid_sync();
     if (rank == 0) {
-      const uint32_t id192 = umma_idesc_bf16(256, 192), id128 = umma_idesc_bf16(256, 128);
+      const uint32_t id_w = umma_idesc_bf16(256, WN), id128 = umma_idesc_bf16(256, 128);
       constexpr uint32_t DESC_HI = 64u | (1u << 14) | (2u << 29);          // SBO 1024 B | version 1 | SWIZZLE_128B
       const uint32_t lo_a1 = (smem_u32(a1) >> 4) | (1u << 16);
       const uint32_t lo_a2 = (smem_u32(a2) >> 4) | (1u << 16);
@@ -194,7 +211,7 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_consta
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16_cg2(d, desc(a_lo + 2 * k), desc(lo_w + s * (BT_SLOT >> 4) + 2 * k), idesc, !(first && k == 0));
+            umma_bf16_cg2(d, desc(a_lo + 2 * k), desc(lo_w + s * (SLOT >> 4) + 2 * k), idesc, !(first && k == 0));
           umma_commit_cg2(&w_empty[s]);
         }
         __syncwarp();
@@ -203,10 +220,11 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_consta
       BT_STAMP(0);
       if (with_proj) {
         mbar_wait(a0_full, 0);
+        mbar_wait(x_done, 0);                          // ACC2 holds x + b_proj: the proj product accumulates onto it
         tc_fence_after();
         BT_STAMP(1);
         for (int kb = 0; kb < KB1; ++kb)
-          for (int h = 0; h < NH; ++h) mma_tile(tmem_base + h * 192, lo_a1 + kb * (16384 >> 4), id192, kb == 0);
+          for (int h = 0; h < NSUB; ++h) mma_tile(tmem_base + h * WN, lo_a1 + kb * (16384 >> 4), id_w, false);
         if (elect_one()) umma_commit_cg2(acc0_full);
         __syncwarp();
         BT_STAMP(2);
@@ -224,17 +242,17 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_consta
         __syncwarp();
       };
       auto mma2 = [&](int j) {
-        const int b = j & 1;
-        mbar_wait(&a2_full[b], (j >> 1) & 1);
-        tc_fence_after();
-        for (int kb = 0; kb < 2; ++kb)
-          for (int h = 0; h < NH; ++h)
-            mma_tile(tmem_base + h * 192, lo_a2 + b * (P::A2_BYTES >> 4) + kb * (16384 >> 4), id192, false);   // ACC2 holds the residual
-        if (elect_one()) {
-          umma_commit_cg2(&a2_empty[b]);
-          if (j == NCHUNK - 1) umma_commit_cg2(acc2_full);
+        for (int kb = 0; kb < 2; ++kb) {
+          const int hc = 2 * j + kb, b = hc % 3;      // half-chunk index -> buffer
+          mbar_wait(&a2_full[b], (hc / 3) & 1);
+          tc_fence_after();
+          for (int h = 0; h < NSUB; ++h) mma_tile(tmem_base + h * WN, lo_a2 + b * (16384 >> 4), id_w, false);   // ACC2 holds the residual
+          if (elect_one()) {
+            umma_commit_cg2(&a2_empty[b]);
+            if (j == NCHUNK - 1 && kb == 1) umma_commit_cg2(acc2_full);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       };
       mma1(0);
       for (int j = 0; j < NCHUNK; ++j) {
@@ -254,78 +272,88 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_consta
     const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t rsw = (uint32_t)r & 7u;
     float* s_sum = stats;                        // [128][4]
-    float* s_sq = stats + 512;
+    float* s_sq = stats + 512;                   // [128][4]; holds b_proj until pass 2
     pdl_grid_sync();
     if (ew == 0) BT_STAMP(4);
+    // x + b_proj -> ACC2 (tensor memory): the residual rows stay on chip from here to the final store
+#pragma unroll 1
+    for (int c = part; c < XCH; c += 4) {
+      mbar_wait(&x_full[c], 0);
+      const uint8_t* xb = a2 + (c % 3) * 16384 + r * 128;
+      uint32_t o[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 v = *reinterpret_cast<const float4*>(xb + (((uint32_t)i ^ rsw) << 4));
+        const float4 bp = *reinterpret_cast<const float4*>(s_sq + c * 32 + 4 * i);     // broadcast read
+        o[4 * i] = __float_as_uint(v.x + bp.x); o[4 * i + 1] = __float_as_uint(v.y + bp.y);
+        o[4 * i + 2] = __float_as_uint(v.z + bp.z); o[4 * i + 3] = __float_as_uint(v.w + bp.w);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&x_free[c % 3]);
+      tmem_st_32x32(tl + c * 32, o);
+    }
+    tmem_st_wait();
     if (with_proj) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(x_done, 0);
       mbar_wait(acc0_full, 0);
       tc_fence_after();
     }
     if (ew == 0) BT_STAMP(5);
-    // pass 1: x_new = x + (o . Wproj^T) + b_proj -> back into ACC2; row sum
+    // pass 1: row sum of x_new = x + b_proj + o . Wproj^T (from tensor memory)
     float sum = 0.f;
 #pragma unroll 1
     for (int c = part; c < XCH; c += 4) {
-      uint32_t acc[32];
-      if (with_proj) tmem_ld_32x32(tl + c * 32, acc);
-      mbar_wait(&x_full[c], 0);
-      const uint8_t* xb = a1 + (c % XB) * 16384 + r * 128;
-      float4 xv[8];
+      uint32_t v[32];
+      tmem_ld_32x32(tl + c * 32, v);
+      tmem_ld_wait();
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(xb + (((uint32_t)i ^ rsw) << 4));
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&x_free[c % XB]);
-      if (with_proj) tmem_ld_wait();
-      uint32_t o[32];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 v = xv[i];
-        if (with_proj) {
-          const float4 bp = __ldg(reinterpret_cast<const float4*>(p.b_proj + c * 32) + i);
-          v.x += __uint_as_float(acc[4 * i]) + bp.x; v.y += __uint_as_float(acc[4 * i + 1]) + bp.y;
-          v.z += __uint_as_float(acc[4 * i + 2]) + bp.z; v.w += __uint_as_float(acc[4 * i + 3]) + bp.w;
-        }
-        sum += (v.x + v.y) + (v.z + v.w);
-        o[4 * i] = __float_as_uint(v.x); o[4 * i + 1] = __float_as_uint(v.y);
-        o[4 * i + 2] = __float_as_uint(v.z); o[4 * i + 3] = __float_as_uint(v.w);
+      for (int i = 0; i < 32; i += 4) {
+        s0 += __uint_as_float(v[i]); s1 += __uint_as_float(v[i + 1]); s2 += __uint_as_float(v[i + 2]); s3 += __uint_as_float(v[i + 3]);
       }
-      tmem_st_32x32(tl + c * 32, o);
+      sum += (s0 + s1) + (s2 + s3);
     }
-    tmem_st_wait();
     s_sum[r * 4 + part] = sum;
     if (ew == 0) BT_STAMP(6);
-    named_bar_sync(1, BT_NCW * 32);              // also: every residual chunk has been consumed, the A1 region is free
+    named_bar_sync(1, BT_NCW * 32);              // also: b_proj (in s_sq) is dead from here on
     const float4 ps = *reinterpret_cast<const float4*>(s_sum + r * 4);
     const float mean = ((ps.x + ps.y) + (ps.z + ps.w)) * (1.0f / (float)C);
-    // pass 2: centred sum of squares from tensor memory
+    // pass 2: centred sum of squares
     float sq = 0.f;
 #pragma unroll 1
     for (int c = part; c < XCH; c += 4) {
       uint32_t v[32];
       tmem_ld_32x32(tl + c * 32, v);
       tmem_ld_wait();
+      float q0 = 0.f, q1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float d = __uint_as_float(v[i]) - mean;
-        sq = fmaf(d, d, sq);
+      for (int i = 0; i < 32; i += 2) {
+        const float d0 = __uint_as_float(v[i]) - mean, d1 = __uint_as_float(v[i + 1]) - mean;
+        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
       }
+      sq += q0 + q1;
     }
     s_sq[r * 4 + part] = sq;
     if (ew == 0) BT_STAMP(7);
     named_bar_sync(1, BT_NCW * 32);
     const float4 pq = *reinterpret_cast<const float4*>(s_sq + r * 4);
     const float rstd = 1.0f / sqrtf(((pq.x + pq.y) + (pq.z + pq.w)) * (1.0f / (float)C) + p.eps);
-    // pass 3: normalise -> bf16 -> A1 (K-major, 128-byte rows, 16-byte slots XOR (row & 7))
+    // pass 3: normalise -> bf16 -> A1 (K-major, 128-byte rows, 16-byte slots XOR (row & 7)); the o tile there is dead
+    // (acc0_full), and so are the x chunks in the A2 region (every warp passed the barriers above)
 #pragma unroll 1
     for (int c = part; c < XCH; c += 4) {
       uint32_t v[32];
       tmem_ld_32x32(tl + c * 32, v);
       tmem_ld_wait();
       uint8_t* dst = a1 + (c >> 1) * 16384 + r * 128;
+      const float* gm = par + c * 32;
+      const float* bt = par + C + c * 32;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + c * 32) + 2 * i), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + c * 32) + 2 * i + 1);
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + c * 32) + 2 * i), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + c * 32) + 2 * i + 1);
+        const float4 g0 = *reinterpret_cast<const float4*>(gm + 8 * i), g1 = *reinterpret_cast<const float4*>(gm + 8 * i + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(bt + 8 * i), b1 = *reinterpret_cast<const float4*>(bt + 8 * i + 4);
         const float y0 = (__uint_as_float(v[8 * i]) - mean) * rstd * g0.x + b0.x, y1 = (__uint_as_float(v[8 * i + 1]) - mean) * rstd * g0.y + b0.y;
         const float y2 = (__uint_as_float(v[8 * i + 2]) - mean) * rstd * g0.z + b0.z, y3 = (__uint_as_float(v[8 * i + 3]) - mean) * rstd * g0.w + b0.w;
         const float y4 = (__uint_as_float(v[8 * i + 4]) - mean) * rstd * g1.x + b1.x, y5 = (__uint_as_float(v[8 * i + 5]) - mean) * rstd * g1.y + b1.y;
@@ -339,12 +367,15 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_consta
     __syncwarp();
     if (lane == 0) mbar_arrive_remote(a1_full, 0);
     if (ew == 0) BT_STAMP(8);
+    // b2 for the final epilogue replaces the row sums (every warp has read them: second barrier above)
+    for (int i = threadIdx.x - 64; i < C; i += BT_NCW * 32) s_sum[i] = __ldg(p.b2 + i);
+    named_bar_sync(1, BT_NCW * 32);
 
-    // main loop: GELU of hidden chunk j, this warp's 32 columns of it
+    // main loop: GELU of hidden chunk j, this warp's 32 columns of it (half-chunk part >> 1, 16-byte slots (part & 1) * 4 ..)
     const uint32_t a2_row = (uint32_t)r * 128;
 #pragma unroll 1
     for (int j = 0; j < NCHUNK; ++j) {
-      const int b = j & 1, u = j >> 1;
+      const int hc = 2 * j + (part >> 1), b = hc % 3;
       mbar_wait(acc1_full, j & 1);
       tc_fence_after();
       if (ew == 0) BT_STAMP(80 + 4 * j);
@@ -366,8 +397,8 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_consta
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = gelu_erf_pk2(v[i]);
-      mbar_wait(&a2_empty[b], (u & 1) ^ 1);                 // MMA2(j - 2) has finished reading A2[b]
-      uint8_t* dst = a2 + b * P::A2_BYTES + (part >> 1) * 16384 + a2_row;
+      mbar_wait(&a2_empty[b], ((hc / 3) & 1) ^ 1);          // the MMA2 k-block that last read this buffer has retired
+      uint8_t* dst = a2 + b * 16384 + a2_row;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         *reinterpret_cast<uint4*>(dst + ((((uint32_t)((part & 1) * 4 + i)) ^ rsw) << 4)) =
@@ -379,28 +410,27 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_consta
       if (ew == 0) BT_STAMP(80 + 4 * j + 1);
     }
 
-    // final epilogue: x = ACC2 + b2 (ACC2 = residual + fc2 product).  Each warp parks 32x32 fp32 chunks in the A2 region (every
-    // MMA2 has retired) in the TMA swizzle pattern and stores them; rows past M are clipped by the TMA unit.
+    // final epilogue: x = ACC2 + b2 (ACC2 = residual + fc2 product).  Each warp parks 32x32 fp32 chunks in shared memory (the A1
+    // region: every MMA1 has retired) in the TMA swizzle pattern and stores them; rows past M are clipped by the TMA unit.
     mbar_wait(acc2_full, 0);
     tc_fence_after();
     if (ew == 0) BT_STAMP(9);
-    uint8_t* sb = a2 + ew * 4096;
+    uint8_t* sb = a1 + ew * 4096;
     const uint32_t srow = (uint32_t)lane * 128u, sswz = (uint32_t)lane & 7u;
 #pragma unroll 1
     for (int c = part; c < XCH; c += 4) {
       uint32_t rg[32];
       tmem_ld_32x32(tl + c * 32, rg);
-      float4 bb[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) bb[i] = __ldg(reinterpret_cast<const float4*>(p.b2 + c * 32) + i);
       if (lane == 0) bulk_wait_read<0>();      // this warp's previous store has left its staging buffer
       __syncwarp();
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i) {
+        const float4 bb = *reinterpret_cast<const float4*>(s_sum + c * 32 + 4 * i);
         *reinterpret_cast<float4*>(sb + srow + (((uint32_t)i ^ sswz) << 4)) =
-            make_float4(__uint_as_float(rg[4 * i]) + bb[i].x, __uint_as_float(rg[4 * i + 1]) + bb[i].y,
-                        __uint_as_float(rg[4 * i + 2]) + bb[i].z, __uint_as_float(rg[4 * i + 3]) + bb[i].w);
+            make_float4(__uint_as_float(rg[4 * i]) + bb.x, __uint_as_float(rg[4 * i + 1]) + bb.y,
+                        __uint_as_float(rg[4 * i + 2]) + bb.z, __uint_as_float(rg[4 * i + 3]) + bb.w);
+      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -431,7 +461,7 @@ static int launch_swin_tail(const TailParams& p, const void* o, float* x, long l
     cudaError_t e = cudaFuncSetAttribute(swin_tail_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM);
     if (e != cudaSuccess) return (int)e;
   }
-  CUtensorMap to, tx, tw96, tw2, tw1;
+  CUtensorMap to, tx, twp, tw2, tw1;
   int rc;
   if (o) {
     if ((rc = make_tmap(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, o, p.M, C, C, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -440,10 +470,10 @@ static int launch_swin_tail(const TailParams& p, const void* o, float* x, long l
   if ((rc = make_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, p.M, C, ldx, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) != MVLT_OK) return rc;
   if (!o) to = tx;                               // unused when with_proj == 0 (must still be a valid encoding)
-  // proj weight [C, C]: tiles of [96 rows, 64 k]; fc2 weight [C, 4C]: same tile shape; fc1 weight [4C, C]: tiles of [64 rows, 64 k]
-  if ((rc = make_tmap(&tw96, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wproj ? wproj : w2, C, wproj ? C : P::HID, wproj ? C : P::HID, 64, 96,
+  // proj weight [C, C] and fc2 weight [C, 4C]: tiles of [WROWS rows, 64 k]; fc1 weight [4C, C]: tiles of [64 rows, 64 k]
+  if ((rc = make_tmap(&twp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wproj ? wproj : w2, C, wproj ? C : P::HID, wproj ? C : P::HID, 64, P::WROWS,
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != MVLT_OK) return rc;
-  if ((rc = make_tmap(&tw2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w2, C, P::HID, P::HID, 64, 96, CU_TENSOR_MAP_SWIZZLE_128B,
+  if ((rc = make_tmap(&tw2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w2, C, P::HID, P::HID, 64, P::WROWS, CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != MVLT_OK) return rc;
   if ((rc = make_tmap(&tw1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w1, P::HID, C, C, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != MVLT_OK) return rc;
@@ -464,7 +494,7 @@ static int launch_swin_tail(const TailParams& p, const void* o, float* x, long l
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = mvlt_pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, swin_tail_kernel<C>, to, tx, tx32, tw96, tw2, tw1, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, swin_tail_kernel<C>, to, tx, tx32, twp, tw2, tw1, p);
   return e == cudaSuccess ? MVLT_OK : (int)e;
 }
 
