@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-retrieval", action="store_true", help="skip the bounded config-4 sub-run at world > 1")
     return ap.parse_args()
 
 
@@ -388,6 +389,45 @@ def parity_report(model, x, ids, rows=64):
             "meets_1e-2": bool(rel <= 1e-2)}
 
 
+def retrieval_subrun(world, rank, dev, L):
+    """BASELINE.json configs[3] at a bounded size inside the scaling run (world > 1): 8*R images x 500 captions, rows of the
+    pair matrix sharded by image over the R ranks, ONE NCCL all-gather of the fp32 score slabs, ranks on rank 0.
+    -> pairs/s (device events, max over ranks), the all-gather's own device time, and whether the sharded + gathered
+    matrix equals rank 0 scoring every row alone, bit for bit."""
+    import torch
+    import torch.distributed as dist
+    from medical_vision_langauge_transformer_b200 import retrieval, synth
+    from medical_vision_langauge_transformer_b200.modules import config as C, model as M
+    torch.manual_seed(0)
+    model = M.MVLBertForRetrieval(C.offline_config("retrieval", max_length=L)).eval().to(dev).set_precision("bf16")
+    n_img, n_cap, pb = 8 * world, 500, 2000
+    imgs, caps = synth.synth_images(n_img, 7, 0.02), synth.synth_token_ids(n_cap, L, 7)
+    labels = torch.zeros(n_img, n_cap)
+    labels[torch.arange(n_img), torch.arange(n_img) % n_cap] = 1
+    retrieval.rank_task(model, imgs, caps, labels, rank, world, pb)            # warm-up (graph capture, NCCL)
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    timing = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    full, metrics = retrieval.rank_task(model, imgs, caps, labels, rank, world, pb, timing=timing)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ag = timing["allgather_events"]
+    t = torch.tensor([e0.elapsed_time(e1), ag[0].elapsed_time(ag[1]) * 1e3], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    same = None
+    if rank == 0:
+        alone = retrieval.score_matrix(model, imgs, caps, 0, 1, pb)
+        same = bool(torch.equal(alone, full))
+    dist.barrier()
+    if rank != 0:
+        return None
+    return {"workload": f"{n_img} x {n_cap} pairs, L={L}, rows sharded over {world} ranks, one all-gather", "pairs_per_s": n_img * n_cap / t[0].item() * 1e3,
+            "ms": t[0].item(), "allgather_us": t[1].item(), "allgather_bytes_per_rank": timing["allgather_bytes_per_rank"],
+            "bit_identical_to_single_rank": same, "R@1_i2t": metrics["i2t_retrieval"]["R@1"]}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -502,6 +542,9 @@ def run_ours(args):
         eager = gpu_eager_baseline(model, d_imgs[0], d_ids[0], local)
     if rank == 0 and world == 1 and not args.no_parity and args.precision == "bf16":
         parity = parity_report(model, d_imgs[0], d_ids[0])
+    retr = None
+    if world > 1 and not args.no_retrieval and args.precision == "bf16" and args.conv == "swintransformer":
+        retr = retrieval_subrun(world, rank, dev, L)
 
     if rank == 0:
         pairs = world * B * args.steps
@@ -539,6 +582,8 @@ def run_ours(args):
             res["gpu_eager_baseline"] = eager
         if parity:
             res["parity"] = parity
+        if retr:
+            res["retrieval_rank"] = retr
         print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()

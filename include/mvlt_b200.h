@@ -172,7 +172,7 @@ int mvlt_window_attention_tc(const void* qkv, void* out, const float* bias_table
 int mvlt_joint_embed(const void* feat, int feat_dtype, const int* img_index, const long long* ids,
                      const unsigned char* text_mask, const unsigned char* image_mask, const float* word_emb,
                      const float* typepos, void* out, int out_dtype, void* out_bf16_copy, float* kmask, int B, int n_obj,
-                     int L, int D, int cls_id, int sep_id, mvlt_stream_t stream);
+                     int L, int D, int cls_id, int sep_id, int vocab_rows, mvlt_stream_t stream);
 
 /* ViT token assembly (torchvision vision_transformer.py `_process_input` + class token + pos_embedding, vfe.py:94-107):
  * out fp32 [B, 1 + n_patch, D]; out[b,0] = cls + pos[0]; out[b,1+i] = patches[b*n_patch + i] + pos[1+i]. */
@@ -192,6 +192,18 @@ int mvlt_joint_attention(const void* qkv, void* out, int dtype, const float* kma
  * caller uses mvlt_joint_attention. */
 int mvlt_joint_attention_tc(const void* qkv, void* out, const float* kmask, int B, int S, int heads, int head_dim, int seq2seq,
                             int obj_end, float scale, mvlt_stream_t stream);
+
+/* Masked-LM loss WITHOUT the logits (model.py:396-410: BertOnlyMLMHead decoder, HF modeling_bert.py:502-512, + CrossEntropyLoss with
+ * ignore_index): the vocabulary GEMM t[rows,K] . w[N,K]^T + bias runs on the tcgen05 kernel with an online-logsumexp epilogue that
+ * writes one (max, sum exp) pair per (row, 256-column tile, epilogue part) instead of the [rows, N] fp32 logits (312 MB at batch 32);
+ * a finishing pass combines them, recomputes logits[label] from the bf16 operands, and reduces in a fixed order:
+ * loss_sum[0] = sum of per-row losses over rows with label != ignore_index, loss_sum[1] = their number.  A label outside [0, N)
+ * makes the loss NaN.  t, w bf16 (row strides ldt, ldw), bias fp32 or NULL, labels int64 [rows]; workspace (caller-owned,
+ * 16-byte aligned) of mvlt_mlm_ce_workspace_bytes(rows, N) bytes. */
+long long mvlt_mlm_ce_workspace_bytes(long long rows, int N);
+int mvlt_mlm_ce_fused(const void* t, long long ldt, const void* w, long long ldw, const float* bias, const long long* labels,
+                      float* loss_sum, void* workspace, long long workspace_bytes, long long rows, int N, int K,
+                      long long ignore_index, mvlt_stream_t stream);
 
 /* out[r, n] = x[r,:] . w[n,:] + bias[n], N <= 16 (fp32 weights/outputs).  model.py:435, :363. */
 int mvlt_linear_small(const void* x, int x_dtype, long long ldx, const float* w, const float* bias, float* out,

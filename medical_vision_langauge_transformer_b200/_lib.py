@@ -35,7 +35,8 @@ PROTOTYPES = {
     "mvlt_joint_attention_tc": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp],
     "mvlt_patch_merge_ln": [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "mvlt_window_attention": [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
-    "mvlt_joint_embed": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "mvlt_joint_embed": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mvlt_mlm_ce_fused": [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _ll, _i, _i, _ll, _vp],
     "mvlt_vit_embed": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "mvlt_joint_attention": [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _f, _vp],
     "mvlt_linear_small": [_vp, _i, _ll, _vp, _vp, _vp, _ll, _i, _i, _vp],
@@ -69,6 +70,8 @@ def load() -> C.CDLL:
                 fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
                 fn.argtypes = argtypes
                 fn.restype = C.c_int
+            lib.mvlt_mlm_ce_workspace_bytes.argtypes = [_ll, _i]
+            lib.mvlt_mlm_ce_workspace_bytes.restype = C.c_longlong
             _lib = lib
     return _lib
 

@@ -327,7 +327,9 @@ template <int SP, int NS> struct JtPlan {
   static constexpr int V_BYTES = NS * KV_BYTES;                   // released when P.V has retired
   static constexpr int MASK_FLOATS = JT_SLOTS * NS * SP;
   static constexpr int STAGING_BYTES = JT_WG_WARPS * JT_SLOTS * 2048;   // one [32 rows x 64 B] output tile per softmax warp
-  static constexpr int XCH_FLOATS = JT_SLOTS * 2 * 256;           // per slot: partial row maxima [128][2], partial row sums [128][2]
+  static constexpr int NCS = SP / 16;                             // 16-key chunks of a score row
+  static constexpr int XCH_SLOT = 256 + 128 * (SP / 16);          // per slot: partial row maxima [128][2], per-chunk row sums [128][NCS]
+  static constexpr int XCH_FLOATS = JT_SLOTS * XCH_SLOT;
   static constexpr int KSPLIT = SP == 144 ? 80 : 48;              // keys [0, KSPLIT) -> thread half 0, [KSPLIT, SP) -> half 1
   static constexpr int SMEM = JT_SLOTS * (QK_BYTES + V_BYTES) + STAGING_BYTES + (MASK_FLOATS + XCH_FLOATS) * 4 + 9 * JT_SLOTS * 8 + 16 + 1024;
   static_assert(KSPLIT % 16 == 0 && (SP - KSPLIT) % 16 == 0, "each half is a whole number of 16-column TMEM loads");
@@ -560,8 +562,9 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const int r = quarter * 32 + lane;
     const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 256;
     float* msk = mask_s + slot * NS * SP;
-    float* x_max = xch + slot * 512;                 // [128][2]
-    float* x_sum = x_max + 256;                      // [128][2]
+    constexpr int NCS = P::NCS;
+    float* x_max = xch + slot * P::XCH_SLOT;         // [128][2]
+    float* x_cs = x_max + 256;                       // [128][NCS]: sum of exp over each 16-key chunk of the row
     uint8_t* stg = staging + (warp - JT_SOFTMAX_WARP0) * 2048;     // this warp's output tile: 32 rows x 64 B, SWIZZLE_64B
     const uint32_t stg_row = (uint32_t)lane * 64u, stg_swz = ((uint32_t)lane >> 1) & 3u;
     const bool s2s = p.seq2seq != 0;
@@ -602,8 +605,10 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       if (wsub == 1) JT_STAMP(n, 7);
       // pass 2: exp2((v - max) * log2e), partial row sum; P as bf16 pairs, held in registers until every thread of the slot
       // has finished reading the score columns
+      // The row sum is accumulated per 16-key chunk and the chunk sums are added in key order by BOTH threads of the row, so the
+      // result does not depend on where the keys are split between them (nor on SP: padded chunks add exact zeros) — a
+      // sequence and its [PAD]-extended copy give bit-identical rows
       const float nmx = -mx * AT_LOG2E;
-      float sum0 = 0.f, sum1 = 0.f;
       uint32_t pk[NK0 / 2];
 #pragma unroll
       for (int cc = 0; cc < NK0 / 16; ++cc) {
@@ -613,15 +618,16 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           tmem_ld_32x16(tl + k_lo + cc * 16, a);
           tmem_ld_wait();
           jt_scores<16>(a, v, mrow, p.scale, s2s, k_lo + cc * 16, i, p.obj_end);
+          float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
           for (int c = 0; c < 16; c += 2) {
             const float e0 = at_ex2(fmaf(v[c], AT_LOG2E, nmx)), e1 = at_ex2(fmaf(v[c + 1], AT_LOG2E, nmx));
             sum0 += e0; sum1 += e1;
             pk[cc * 8 + (c >> 1)] = pack_bf16x2(e0, e1);
           }
+          x_cs[r * NCS + (k_lo >> 4) + cc] = sum0 + sum1;
         }
       }
-      x_sum[r * 2 + half] = sum0 + sum1;
       named_bar_sync(1 + slot, JT_WG_WARPS * 32);
       // P columns: key pair (2q, 2q + 1) -> TMEM column q of the slot (aliasing the score columns, now dead)
 #pragma unroll
@@ -637,7 +643,10 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[slot]);
-      const float inv = 1.0f / ((sum0 + sum1) + x_sum[r * 2 + (half ^ 1)]);
+      float rsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCS; ++c) rsum += x_cs[r * NCS + c];
+      const float inv = 1.0f / rsum;
       if (wsub == 1) JT_STAMP(n, 8);
 
       mbar_wait(&o_full[slot], u & 1);

@@ -85,6 +85,10 @@ struct GemmParams {
   // output pixel (n, p, q) = unflatten(m; Ho*Wo, Wo) and k-block kb covers tap kb / conv_cpb = (ky, kx), channels
   // 64 * (kb % conv_cpb) .. +64 (the weight is packed tap-major: [N, R*S*C])
   int conv_cpb, conv_s, conv_wo, conv_howo, conv_stride, conv_pad;
+  // ACT 5 (fused vocabulary projection + cross-entropy, model.py:396-410): instead of storing the [M, N] logits the epilogue
+  // keeps a running (max, sum of exp) per row over each warp's chunks of a tile and writes ONE float2 per (row, tile, part)
+  float2* lse_part;     // [M][lse_ld] (max, sum exp(x - max)) partials
+  int lse_ld;           // = tiles_n * EPI_PARTS
   unsigned long long* trace;  // debug: clock64 stamps of CTA 0 (tools/gemm_trace.py); nullptr in production
 };
 static unsigned long long* g_gemm_trace = nullptr;
@@ -98,7 +102,8 @@ __global__ void __launch_bounds__((Plan<OUT_BF16, RES, DEEP>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, GemmParams p) {
   static_assert(!(RES == 2 && OUT_BF16), "reduce-add epilogue is fp32");
-  static_assert(ACT < 3 || OUT_BF16, "ReLU epilogues are bf16-out");
+  static_assert(ACT < 3 || ACT == 5 || OUT_BF16, "ReLU epilogues are bf16-out");
+  static_assert(ACT != 5 || (!OUT_BF16 && RES == 0), "the logsumexp epilogue has no output tile and no residual");
   constexpr uint32_t RES_CHUNK_BYTES = 32 * 32 * (OUT_BF16 ? 2 : 4);
   using P = Plan<OUT_BF16, RES, DEEP>;
   constexpr int STAGES = P::STAGES, EPI_NBUF = P::NBUF, EPI_BUF_BYTES = P::BUF_BYTES, RING_BYTES = P::RING_BYTES;
@@ -303,6 +308,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     };
     int k = 0;
     uint32_t res_parity = 0;  // bit b: parity of the next residual load to land in staging buffer b
+    float lse_m = -INFINITY, lse_s = 0.f;   // ACT 5: running row maximum / sum of exp over this warp's chunks of the tile
     for (; cur.ti < my_tiles; ++k) {
       const int ti = cur.ti, c = cur.c;
       const int buf = k % EPI_NBUF;
@@ -366,7 +372,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         } else if (ACT == 2) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = make_float2(tanhf(v[i].x), tanhf(v[i].y));
-        } else if (ACT >= 3 && RES == 0) {
+        } else if ((ACT == 3 || ACT == 4) && RES == 0) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             v[i] = make_float2(fmaxf(v[i].x, 0.f), fmaxf(v[i].y, 0.f));
@@ -374,6 +380,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         if (tr_on) GEMM_STAMP(256 + 8 * k + 4);
+        if (ACT == 5) {
+          // online logsumexp over the chunk's (valid) columns; columns past N carry zero-filled operands: excluded
+          const int ncol = p.N - n0;
+          float cm = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (2 * i < ncol) cm = fmaxf(cm, v[i].x);
+            if (2 * i + 1 < ncol) cm = fmaxf(cm, v[i].y);
+          }
+          const float L2E = 1.4426950408889634f, nm = -cm * L2E;
+          float cs = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float e0, e1;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(v[i].x, L2E, nm)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(v[i].y, L2E, nm)));
+            if (2 * i < ncol) cs += e0;
+            if (2 * i + 1 < ncol) cs += e1;
+          }
+          const float nmx = fmaxf(lse_m, cm);
+          float a0, a1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a0) : "f"((lse_m - nmx) * L2E));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a1) : "f"((cm - nmx) * L2E));
+          lse_s = lse_s * a0 + cs * a1;
+          lse_m = nmx;
+        }
+        if (ACT != 5) {
         if (RES != 1) {  // buffer k % NBUF was last read by the store of step k - NBUF
           if (elect_one()) bulk_wait_read<EPI_NBUF - 1>();
           __syncwarp();
@@ -422,10 +455,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         if (tr_on) GEMM_STAMP(256 + 8 * k + 5);
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA unit
+        }  // ACT != 5
       }
       __syncwarp();
       if (tr_on) GEMM_STAMP(256 + 8 * k + 6);
-      if (elect_one()) {
+      if (ACT == 5) {
+        // last chunk of this warp in the tile: one (max, sum) pair per row and (tile column, part)
+        if (!has_next || nxt.ti != ti) {
+          const int tile = group + ti * num_groups;
+          const int tn = tile % p.tiles_n;
+          const int row = m0 + lane;
+          if (row < p.M) p.lse_part[(long long)row * p.lse_ld + tn * EPI_PARTS + part] = make_float2(lse_m, lse_s);
+          lse_m = -INFINITY; lse_s = 0.f;
+        }
+      } else if (elect_one()) {
         if (live) {
           if (RES == 2) tma_reduce_add_2d(&tmap_c, sb, n0, m0); else tma_store_2d(&tmap_c, sb, n0, m0);
         }
@@ -474,6 +517,7 @@ template <int ACT, bool OUT_BF16, int RES, bool DEEP> static Variant variant() {
 // act 0..2: res 0..2 with fp32 C, res 0 with bf16 C; deep only with res != 0 and act == 0.  act 3/4 (ReLU epilogues): bf16 C
 // with res 0 or 1 (bf16 residual).  Returns a null kernel for combinations that are not compiled.
 static Variant pick_variant(int act, bool out_bf16, int res, bool deep) {
+  if (act == 5) return (!out_bf16 && res == 0 && !deep) ? variant<5, false, 0, false>() : Variant{nullptr, 0, 0};
 #define MVLT_ACT(O, R, D) (act == 0 ? variant<0, O, R, D>() : act == 1 ? variant<1, O, R, D>() : variant<2, O, R, D>())
   if (act >= 3) {
     if (!out_bf16 || res == 2) return Variant{nullptr, 0, 0};
@@ -503,7 +547,7 @@ static int gemm_tc_init() {
     g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn2);
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   }
-  for (int act = 0; act < 5; ++act)
+  for (int act = 0; act < 6; ++act)
     for (int o = 0; o < 2; ++o)
       for (int r = 0; r < 3; ++r)
         for (int d = 0; d < 2; ++d) {
@@ -589,11 +633,11 @@ static int make_tmap_im2col(CUtensorMap* map, const void* x, const ConvGeom& g) 
 
 static int gemm_launch(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc,
                        const float* bias, const void* residual, long long ldres, int res_dtype, int M, int N, int K,
-                       int act, int out_dtype, int block_n, const ConvGeom* conv, cudaStream_t stream) {
+                       int act, int out_dtype, int block_n, const ConvGeom* conv, cudaStream_t stream, float2* lse_part = nullptr) {
   if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0) return MVLT_ERR_INVALID;
   if (K % 16 != 0 || ldw % 8 != 0 || (!conv && lda % 8 != 0)) return MVLT_ERR_INVALID;  // TMA: 16 B aligned rows
   if (((uintptr_t)A & 15) || ((uintptr_t)W & 15) || ((uintptr_t)C & 15)) return MVLT_ERR_INVALID;
-  if (act < 0 || act > 4 || (out_dtype != MVLT_F32 && out_dtype != MVLT_BF16)) return MVLT_ERR_INVALID;
+  if (act < 0 || act > 5 || (act == 5) != (lse_part != nullptr) || (out_dtype != MVLT_F32 && out_dtype != MVLT_BF16)) return MVLT_ERR_INVALID;
   const bool out_bf16 = out_dtype == MVLT_BF16;
   if (ldc % (out_bf16 ? 8 : 4) != 0) return MVLT_ERR_INVALID;                // TMA store: 16 B aligned rows
   if (bias && ((uintptr_t)bias & 15)) return MVLT_ERR_INVALID;
@@ -643,6 +687,8 @@ static int gemm_launch(const void* A, long long lda, const void* W, long long ld
     p.conv_stride = conv->stride; p.conv_pad = conv->pad;
   }
   p.trace = g_gemm_trace;
+  p.lse_part = lse_part;
+  p.lse_ld = p.tiles_n * 2;   // Plan<false, 0, false>::EPI_PARTS
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = CG * (tiles < groups ? tiles : groups);
 
@@ -686,4 +732,17 @@ extern "C" int mvlt_conv2d_nhwc_bf16_tc(const void* x, int B, int H, int W, int 
   if (M > 0x7fffffffLL) return MVLT_ERR_UNSUPPORTED;
   return gemm_launch(x, 0, w, ldw, out, ldc, bias, residual, ldres, MVLT_BF16, (int)M, N, R * S * C, act, MVLT_BF16, block_n, &g,
                      stream);
+}
+
+// Fused vocabulary projection + logsumexp (the MLM decoder of HF modeling_bert.py:502-512 feeding the cross-entropy of model.py:404-410):
+// part[m][t * 2 + e] = (max, sum exp(x - max)) of the logits A[m,:] . W[n,:]^T + bias[n] over the columns of tile t handled by epilogue
+// part e — the [M, N] logits (312 MB fp32 at batch 32) are never written.  ld_part >= 2 * ceil(N / 256) float2 per row.
+extern "C" int mvlt_gemm_bf16_lse_partials(const void* A, long long lda, const void* W, long long ldw, const float* bias, void* part,
+                                           long long ld_part, int M, int N, int K, cudaStream_t stream) {
+  if (!part || ((uintptr_t)part & 15)) return MVLT_ERR_INVALID;
+  const int tiles_n = (N + 255) / 256;
+  if (ld_part != 2LL * tiles_n) return MVLT_ERR_INVALID;
+  // the (unused) C tensor map is encoded over the partials buffer viewed as fp32 [M, 2 * ld_part]
+  return gemm_launch(A, lda, W, ldw, part, 2 * ld_part, bias, nullptr, 0, -1, M, N, K, 5, MVLT_F32, 256, nullptr, stream,
+                     reinterpret_cast<float2*>(part));
 }

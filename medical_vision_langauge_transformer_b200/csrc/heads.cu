@@ -58,6 +58,10 @@ masked_ce_rows_kernel(const float* __restrict__ logits, long long ld, const long
   const int lane = threadIdx.x & 31;
   const long long lab = labels[row];
   if (lab == ignore) return;
+  if (lab < 0 || lab >= N) {      // F.cross_entropy raises here; a kernel cannot: poison the loss instead of reading out of bounds
+    if (lane == 0) atomicAdd(&loss_sum[0], __int_as_float(0x7fc00000));
+    return;
+  }
   const float* r = logits + row * ld;
   float mx = -INFINITY;
   for (int j = lane; j < N; j += 32) mx = fmaxf(mx, r[j]);
@@ -69,6 +73,58 @@ masked_ce_rows_kernel(const float* __restrict__ logits, long long ld, const long
     atomicAdd(&loss_sum[0], logf(sum) + mx - r[lab]);
     atomicAdd(&loss_sum[1], 1.0f);
   }
+}
+
+// Finishing pass of the fused vocabulary projection + cross-entropy (model.py:404-410): per labelled row
+//   loss = logsumexp(logits) - logits[label],  logsumexp from the GEMM epilogue's (max, sum exp) partials,
+//   logits[label] = t[row,:] . W[label,:] + bias[label] recomputed from the bf16 operands (fp32 accumulate, as the GEMM does).
+// Rows with label == ignore contribute nothing; a label outside [0, N) poisons the loss with NaN (F.cross_entropy raises).
+__global__ void __launch_bounds__(256)
+mlm_ce_rows_kernel(const float2* __restrict__ part, long long ld_part, int n_part, const bf16* __restrict__ t, long long ldt,
+                   const bf16* __restrict__ w, long long ldw, const float* __restrict__ bias, const long long* __restrict__ labels,
+                   float* __restrict__ row_loss, long long rows, int N, int K, long long ignore) {
+  pdl_grid_sync();
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const long long lab = labels[row];
+  if (lab == ignore) { if (lane == 0) row_loss[row] = 0.f; return; }
+  if (lab < 0 || lab >= N) { if (lane == 0) row_loss[row] = __int_as_float(0x7fc00000); return; }
+  const float2* pr = part + row * ld_part;
+  float mx = -INFINITY;
+  for (int j = lane; j < n_part; j += 32) mx = fmaxf(mx, pr[j].x);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < n_part; j += 32) sum += pr[j].y * expf(pr[j].x - mx);
+  sum = warp_sum(sum);
+  float dot = 0.f;
+  const bf16* tr = t + row * ldt;
+  const bf16* wr = w + lab * ldw;
+  for (int k = lane * 2; k < K; k += 64) {
+    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(tr + k)), b = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(wr + k));
+    dot = fmaf(a.x, b.x, dot);
+    dot = fmaf(a.y, b.y, dot);
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) row_loss[row] = logf(sum) + mx - (dot + (bias ? bias[lab] : 0.f));
+}
+
+// deterministic reduction of the per-row losses: one CTA, fixed order -> (sum over labelled rows, number of labelled rows)
+__global__ void __launch_bounds__(256)
+ce_reduce_kernel(const float* __restrict__ row_loss, const long long* __restrict__ labels, float* __restrict__ loss_sum, long long rows,
+                 long long ignore) {
+  pdl_grid_sync();
+  __shared__ float s_l[256], s_c[256];
+  float l = 0.f, c = 0.f;
+  for (long long i = threadIdx.x; i < rows; i += 256)
+    if (labels[i] != ignore) { l += row_loss[i]; c += 1.f; }
+  s_l[threadIdx.x] = l; s_c[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { s_l[threadIdx.x] += s_l[threadIdx.x + o]; s_c[threadIdx.x] += s_c[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { loss_sum[0] = s_l[0]; loss_sum[1] = s_c[0]; }
 }
 
 // Position of the first positive of one line of the score matrix in descending order.  np.argsort(sim)[::-1] lists equal
@@ -149,6 +205,36 @@ extern "C" int mvlt_masked_ce_rows(const float* logits, long long ld, const long
   cudaError_t e = cudaMemsetAsync(loss_sum, 0, 2 * sizeof(float), stream);
   if (e != cudaSuccess) return (int)e;
   launch_k(masked_ce_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, stream, logits, ld, labels, loss_sum, rows, N, ignore_index);
+  MVLT_LAUNCH_CHECK();
+  return MVLT_OK;
+}
+
+extern "C" int mvlt_gemm_bf16_lse_partials(const void* A, long long lda, const void* W, long long ldw, const float* bias, void* part,
+                                           long long ld_part, int M, int N, int K, cudaStream_t stream);
+
+extern "C" long long mvlt_mlm_ce_workspace_bytes(long long rows, int N) {
+  const long long tiles_n = (N + 255) / 256;
+  return rows * 2 * tiles_n * 8 + ((rows * 4 + 15) / 16) * 16;      // (max, sum) partials + per-row losses
+}
+
+// Masked-LM loss without the logits: t bf16 [rows, K] (transformed + normalised text rows), w bf16 [N, K] (decoder weight),
+// bias fp32 [N], labels int64 [rows] -> loss_sum[0] = sum of per-row cross-entropies over rows with label != ignore_index,
+// loss_sum[1] = their count.  workspace: mvlt_mlm_ce_workspace_bytes(rows, N) bytes, 16-byte aligned.  Replaces the decoder
+// nn.Linear(768, vocab) of HF modeling_bert.py:502-512 + nn.CrossEntropyLoss(ignore_index=-100) of model.py:404-410.
+extern "C" int mvlt_mlm_ce_fused(const void* t, long long ldt, const void* w, long long ldw, const float* bias, const long long* labels,
+                                 float* loss_sum, void* workspace, long long workspace_bytes, long long rows, int N, int K,
+                                 long long ignore_index, cudaStream_t stream) {
+  if (!t || !w || !labels || !loss_sum || !workspace || rows <= 0 || N <= 0 || K <= 0 || K % 2) return MVLT_ERR_INVALID;
+  if (rows > 0x7fffffffLL || workspace_bytes < mvlt_mlm_ce_workspace_bytes(rows, N) || ((uintptr_t)workspace & 15)) return MVLT_ERR_INVALID;
+  const long long tiles_n = (N + 255) / 256, ld_part = 2 * tiles_n;
+  float* row_loss = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + rows * ld_part * 8);
+  int rc = mvlt_gemm_bf16_lse_partials(t, ldt, w, ldw, bias, workspace, ld_part, (int)rows, N, K, stream);
+  if (rc != MVLT_OK) return rc;
+  launch_k(mlm_ce_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, stream, reinterpret_cast<const float2*>(workspace), ld_part,
+           (int)ld_part, reinterpret_cast<const bf16*>(t), ldt, reinterpret_cast<const bf16*>(w), ldw, bias, labels, row_loss, rows, N, K,
+           ignore_index);
+  MVLT_LAUNCH_CHECK();
+  launch_k(ce_reduce_kernel, dim3(1), dim3(256), 0, stream, (const float*)row_loss, labels, loss_sum, rows, ignore_index);
   MVLT_LAUNCH_CHECK();
   return MVLT_OK;
 }

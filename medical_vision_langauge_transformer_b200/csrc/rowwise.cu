@@ -391,7 +391,7 @@ joint_embed_kernel(const TF* __restrict__ feat, const int* __restrict__ img_inde
                    const unsigned char* __restrict__ text_mask, const unsigned char* __restrict__ image_mask,
                    const float* __restrict__ word_emb, const float* __restrict__ typepos, TO* __restrict__ out,
                    bf16* __restrict__ out_copy, float* __restrict__ kmask, int B, int n_obj, int L, int D, int cls_id,
-                   int sep_id) {
+                   int sep_id, int vocab_rows) {
   pdl_grid_sync();
   const int S = n_obj + 2 + L;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -423,12 +423,17 @@ joint_embed_kernel(const TF* __restrict__ feat, const int* __restrict__ img_inde
       id = ids[(long long)b * L + (s - n_obj - 2)];
       keep = text_mask ? text_mask[(long long)b * L + (s - n_obj - 2)] != 0 : id > 0;  // model.py:337 (ids > 0)
     }
-    const float* e = word_emb + id * D;
+    // nn.Embedding raises on an id outside the table; a kernel cannot: the row becomes NaN instead of an out-of-bounds read
+    const bool id_ok = id >= 0 && id < vocab_rows;
+    const float* e = word_emb + (id_ok ? id : 0) * D;
+    const float poison = id_ok ? 0.f : __int_as_float(0x7fc00000);
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int c = (lane + 32 * i) * 4;
       if (c < D) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(e + c)), t = __ldg(reinterpret_cast<const float4*>(tp + c));
+        float4 a = __ldg(reinterpret_cast<const float4*>(e + c));
+        const float4 t = __ldg(reinterpret_cast<const float4*>(tp + c));
+        a.x += poison;
         const float4 r = make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w);
         store4(o + c, r);
         if (o2) store4(o2 + c, r);
@@ -569,16 +574,16 @@ extern "C" int mvlt_patch_merge_ln(const float* x, void* out, int out_dtype, con
 extern "C" int mvlt_joint_embed(const void* feat, int feat_dtype, const int* img_index, const long long* ids,
                                 const unsigned char* text_mask, const unsigned char* image_mask, const float* word_emb,
                                 const float* typepos, void* out, int out_dtype, void* out_bf16_copy, float* kmask, int B,
-                                int n_obj, int L, int D, int cls_id, int sep_id, cudaStream_t stream) {
+                                int n_obj, int L, int D, int cls_id, int sep_id, int vocab_rows, cudaStream_t stream) {
   if (!feat || !ids || !word_emb || !typepos || !out || !kmask || B <= 0 || n_obj <= 0 || L < 0) return MVLT_ERR_INVALID;
   if (D != 768) return MVLT_ERR_UNSUPPORTED;
-  if (feat_dtype != out_dtype) return MVLT_ERR_INVALID;
+  if (feat_dtype != out_dtype || vocab_rows <= 0 || cls_id < 0 || cls_id >= vocab_rows || sep_id < 0 || sep_id >= vocab_rows) return MVLT_ERR_INVALID;
   const long long rows = (long long)B * (n_obj + 2 + L);
   const unsigned grid = (unsigned)((rows + 7) / 8);
   if (out_dtype == MVLT_F32)
-    launch_k(joint_embed_kernel<6, float, float>, dim3(grid), dim3(256), 0, stream, (const float*)feat, img_index, ids, text_mask, image_mask, word_emb, typepos, (float*)out, (bf16*)out_bf16_copy, kmask, B, n_obj, L, D, cls_id, sep_id);
+    launch_k(joint_embed_kernel<6, float, float>, dim3(grid), dim3(256), 0, stream, (const float*)feat, img_index, ids, text_mask, image_mask, word_emb, typepos, (float*)out, (bf16*)out_bf16_copy, kmask, B, n_obj, L, D, cls_id, sep_id, vocab_rows);
   else if (out_dtype == MVLT_BF16)
-    launch_k(joint_embed_kernel<6, bf16, bf16>, dim3(grid), dim3(256), 0, stream, (const bf16*)feat, img_index, ids, text_mask, image_mask, word_emb, typepos, (bf16*)out, (bf16*)out_bf16_copy, kmask, B, n_obj, L, D, cls_id, sep_id);
+    launch_k(joint_embed_kernel<6, bf16, bf16>, dim3(grid), dim3(256), 0, stream, (const bf16*)feat, img_index, ids, text_mask, image_mask, word_emb, typepos, (bf16*)out, (bf16*)out_bf16_copy, kmask, B, n_obj, L, D, cls_id, sep_id, vocab_rows);
   else return MVLT_ERR_INVALID;
   MVLT_LAUNCH_CHECK();
   return MVLT_OK;

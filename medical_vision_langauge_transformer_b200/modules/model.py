@@ -486,10 +486,14 @@ class MVLBertForPretraining(_PackedMixin, MVLBertPretrainedModel):
             t = ops.linear(text, w["tw"], w["tb"], act=ops.ACT_GELU, out_dtype=torch.float32)
             t = ops.layernorm(t, w["lw"], w["lb"], cfg.layer_norm_eps, adt)
             V = w["dw"].shape[0]
-            ld = (V + 31) // 32 * 32
-            logits = torch.empty((B * L, ld), device=t.device, dtype=torch.float32)[:, :V]
-            ops.linear(t, w["dw"], w["db"], out=logits)
-            acc = ops.masked_ce(logits, caption_label.reshape(-1), V, -100)
+            if self.precision == "bf16":
+                # vocabulary GEMM with an online-logsumexp epilogue: the [B*L, vocab] fp32 logits (312 MB at batch 32) are never written
+                acc = ops.mlm_ce_fused(t, w["dw"], w["db"], caption_label.reshape(-1), -100)
+            else:
+                ld = (V + 31) // 32 * 32
+                logits = torch.empty((B * L, ld), device=t.device, dtype=torch.float32)[:, :V]
+                ops.linear(t, w["dw"], w["db"], out=logits)
+                acc = ops.masked_ce(logits, caption_label.reshape(-1), V, -100)
             mlm_loss = acc[0] / acc[1]
         if not cfg.ITM_task:
             return mlm_loss

@@ -423,7 +423,7 @@ def joint_embed(feat: torch.Tensor, ids: torch.Tensor, text_mask: Optional[torch
     copy = torch.empty((B * S, D), device=feat.device, dtype=torch.bfloat16) if bf16_copy else None
     rc = lib.mvlt_joint_embed(feat.data_ptr(), _code(feat), _ptr(img_index), ids.data_ptr(), _ptr(tm), _ptr(im),
                               word_emb.data_ptr(), typepos.data_ptr(), out.data_ptr(), _code(out), _ptr(copy),
-                              kmask.data_ptr(), B, n_obj, L, D, int(cls_id), int(sep_id), _stream())
+                              kmask.data_ptr(), B, n_obj, L, D, int(cls_id), int(sep_id), int(word_emb.shape[0]), _stream())
     _lib.check(rc, "mvlt_joint_embed")
     return out, copy, kmask
 
@@ -492,6 +492,27 @@ def masked_ce(logits: torch.Tensor, labels: torch.Tensor, n_classes: int, ignore
     rc = lib.mvlt_masked_ce_rows(logits.data_ptr(), ld, labels.contiguous().data_ptr(), acc.data_ptr(), rows, n_classes,
                                  ignore_index, _stream())
     _lib.check(rc, "mvlt_masked_ce_rows")
+    return acc
+
+
+def mlm_ce_fused(t: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], labels: torch.Tensor,
+                 ignore_index: int = -100) -> torch.Tensor:
+    """Cross-entropy of the vocabulary projection t @ w.T + bias against labels WITHOUT materialising the logits (tcgen05 GEMM with
+    an online-logsumexp epilogue).  t bf16 [rows, K], w bf16 [N, K] -> fp32 [2]: (sum of per-row losses over rows with
+    label != ignore_index, number of such rows)."""
+    lib = _lib.ensure_init()
+    rows, K, ldt = _rows2d(t)
+    N, Kw, ldw = _rows2d(w)
+    assert t.dtype == w.dtype == torch.bfloat16 and K == Kw
+    assert labels.dtype == torch.int64 and labels.numel() == rows
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
+    nbytes = lib.mvlt_mlm_ce_workspace_bytes(rows, N)
+    ws = torch.empty(nbytes, device=t.device, dtype=torch.uint8)
+    acc = torch.empty(2, device=t.device, dtype=torch.float32)
+    rc = lib.mvlt_mlm_ce_fused(t.data_ptr(), ldt, w.data_ptr(), ldw, _ptr(bias), labels.contiguous().data_ptr(), acc.data_ptr(),
+                               ws.data_ptr(), nbytes, rows, N, K, ignore_index, _stream())
+    _lib.check(rc, f"mvlt_mlm_ce_fused(rows={rows},N={N},K={K})")
     return acc
 
 

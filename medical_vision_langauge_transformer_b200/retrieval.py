@@ -34,12 +34,62 @@ def image_features(model, images: torch.Tensor, chunk: int = 64) -> torch.Tensor
     return torch.cat(outs) if len(outs) > 1 else outs[0]
 
 
+class _PairGraph:
+    """One pair-batch of the scoring loop captured as a CUDA graph over static buffers: pair indices base .. base + PB
+    (row-major enumeration of run_retrieval.py:133-145) -> img_index / caption gather -> joint encoder -> pooler -> head ->
+    softmax -> prob[:, 1] scattered into the padded output; `base` advances by PB inside the graph, so the loop is
+    `replay()` x n_batches with no host work in between (the eager loop spent arange / index_select / empty / slicing per batch)."""
+
+    def __init__(self, model, feats: torch.Tensor, captions: torch.Tensor, pair_batch: int):
+        dev = feats.device
+        n_img, n_cap = feats.shape[0], captions.shape[0]
+        self.P = n_img * n_cap
+        self.PB = pair_batch
+        self.n_batches = -(-self.P // pair_batch)
+        self.out = torch.zeros(self.n_batches * pair_batch, device=dev, dtype=torch.float32)
+        self.base = torch.zeros((), device=dev, dtype=torch.int64)
+        ar = torch.arange(pair_batch, device=dev, dtype=torch.int64)
+        bert = model.MVLBert
+
+        def step():
+            p = self.base + ar
+            pc = p.clamp(max=self.P - 1)                       # the tail batch re-scores the last pair; its slots are padding
+            img_index = torch.div(pc, n_cap, rounding_mode="floor").to(torch.int32)
+            ids = captions.index_select(0, pc - img_index.to(torch.int64) * n_cap)
+            hidden, shadow, B, S = bert.encode(ids, None, feats, None, False, img_index=img_index)
+            prob = ops.softmax_rows(model.head_logits(bert.pool(hidden, shadow, B, S)))
+            self.out.index_copy_(0, p, prob[:, 1].contiguous())
+            self.base.add_(pair_batch)
+
+        self.stream = torch.cuda.Stream(device=dev)
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.stream):
+            step()                                              # warm-up (packs weights, sizes the caching allocator)
+            self.stream.synchronize()
+            self.base.zero_()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                step()
+            self.base.zero_()
+        self.stream.synchronize()
+
+    def run(self) -> torch.Tensor:
+        with torch.cuda.stream(self.stream):
+            for _ in range(self.n_batches):
+                self.graph.replay()
+        torch.cuda.current_stream(self.out.device).wait_stream(self.stream)
+        return self.out[:self.P]
+
+
 @torch.no_grad()
-def score_pairs(model, feats: torch.Tensor, captions: torch.Tensor, pair_batch: int = 512) -> torch.Tensor:
-    """prob[:,1] (run_retrieval.py:204) for every (feature row i, caption j), row-major -> fp32 [n_img, n_cap]."""
+def score_pairs(model, feats: torch.Tensor, captions: torch.Tensor, pair_batch: int = 512, use_graph: bool = True) -> torch.Tensor:
+    """prob[:,1] (run_retrieval.py:204) for every (feature row i, caption j), row-major -> fp32 [n_img, n_cap].
+    use_graph: the pair-batch step is captured once as a CUDA graph and replayed (same kernels, same arithmetic)."""
     n_img, n_cap = feats.shape[0], captions.shape[0]
     dev = feats.device
-    captions = captions.to(dev)
+    captions = captions.to(dev).contiguous()
+    if use_graph and n_img * n_cap >= 2 * pair_batch:
+        return _PairGraph(model, feats.contiguous(), captions, pair_batch).run().view(n_img, n_cap).clone()
     out = torch.empty(n_img * n_cap, device=dev, dtype=torch.float32)
     bert = model.MVLBert
     for p0 in range(0, n_img * n_cap, pair_batch):
@@ -64,8 +114,9 @@ def score_matrix(model, images: torch.Tensor, captions: torch.Tensor, rank: int 
     return score_pairs(model, feats, captions, pair_batch)
 
 
-def all_gather_scores(local: torch.Tensor, n_rows: int, world: int, group=None) -> torch.Tensor:
-    """The single collective of the path: equal-sized (padded) slabs -> [n_rows, n_cap] on every rank."""
+def all_gather_scores(local: torch.Tensor, n_rows: int, world: int, group=None, timing: Optional[dict] = None) -> torch.Tensor:
+    """The single collective of the path: equal-sized (padded) slabs -> [n_rows, n_cap] on every rank.
+    timing (optional dict): receives 'allgather_events' = (start, end) CUDA events around the collective."""
     if world == 1:
         return local
     import torch.distributed as dist
@@ -75,7 +126,15 @@ def all_gather_scores(local: torch.Tensor, n_rows: int, world: int, group=None) 
         padded = torch.zeros(per, local.shape[1], device=local.device, dtype=local.dtype)
         padded[:local.shape[0]] = local
     full = torch.empty(world * per, local.shape[1], device=local.device, dtype=local.dtype)
-    dist.all_gather_into_tensor(full, padded.contiguous(), group=group)
+    padded = padded.contiguous()
+    if timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    dist.all_gather_into_tensor(full, padded, group=group)
+    if timing is not None:
+        e1.record()
+        timing["allgather_events"] = (e0, e1)
+        timing["allgather_bytes_per_rank"] = padded.numel() * padded.element_size()
     return full[:n_rows]
 
 
@@ -117,8 +176,8 @@ def evaluate(scores, labels, ks=(1, 5, 10)) -> dict:
 
 
 def rank_task(model, images: torch.Tensor, captions: torch.Tensor, labels, rank: int = 0, world: int = 1,
-              pair_batch: int = 512, group=None) -> Tuple[torch.Tensor, Optional[dict]]:
+              pair_batch: int = 512, group=None, timing: Optional[dict] = None) -> Tuple[torch.Tensor, Optional[dict]]:
     """Whole `--do_rank` job: shard, score, all-gather, rank on rank 0.  -> (scores [N,N], metrics or None)."""
     local = score_matrix(model, images, captions, rank, world, pair_batch)
-    full = all_gather_scores(local, images.shape[0], world, group)
+    full = all_gather_scores(local, images.shape[0], world, group, timing)
     return full, (evaluate(full, labels) if rank == 0 else None)

@@ -413,6 +413,32 @@ def test_joint_embed_and_attention(cuda, L, seq2seq):
     assert relerr(out16.cpu(), ref) < 1.5e-2
 
 
+@pytest.mark.parametrize("rows,N", [(2560, 30522), (160, 30522), (37, 1000), (300, 256), (5, 33)])
+def test_mlm_ce_fused(cuda, rows, N):
+    """vocabulary GEMM + online-logsumexp epilogue + finishing pass against F.cross_entropy on the fp32 logits of the same bf16
+    operands: ragged vocabulary (30522 = 119 tiles of 256 + 58 columns), ignored rows, deterministic result."""
+    from medical_vision_langauge_transformer_b200 import ops
+    K = 768
+    t = rnd(rows, K, seed=1).bfloat16()
+    w = rnd(N, K, seed=2, scale=2 * K ** -0.5).bfloat16()
+    b = rnd(N, seed=3, scale=0.5)
+    g = torch.Generator().manual_seed(4)
+    labels = torch.randint(0, N, (rows,), generator=g)
+    labels[torch.rand(rows, generator=g) < 0.8] = -100
+    labels[0] = N - 1                                    # a label in the ragged last tile
+    labels = labels.cuda()
+    logits = t.float() @ w.float().t() + b
+    ref_sum = F.cross_entropy(logits, labels, ignore_index=-100, reduction="sum").item()
+    n_lab = int((labels != -100).sum())
+    acc = ops.mlm_ce_fused(t, w, b, labels, -100)
+    assert acc[1].item() == n_lab
+    assert abs(acc[0].item() - ref_sum) < 2e-4 * abs(ref_sum), (acc[0].item(), ref_sum)
+    acc2 = ops.mlm_ce_fused(t, w, b, labels, -100)
+    assert torch.equal(acc, acc2), "fixed-order reduction: bit-identical run to run"
+    bad = labels.clone(); bad[0] = N                    # out-of-range label: NaN, not an out-of-bounds read
+    assert torch.isnan(ops.mlm_ce_fused(t, w, b, bad, -100)[0])
+
+
 def test_heads(cuda):
     from medical_vision_langauge_transformer_b200 import ops
     x = rnd(37, 768, seed=1)

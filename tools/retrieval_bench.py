@@ -6,7 +6,9 @@ ONE all-gather of the fp32 score slabs over NCCL, ranking on rank 0.
 
 Times the job on the device (events around shard scoring + all-gather, max over ranks) and prints scored pairs/s (a
 "pair" = one (image, caption) through the BERT joint encoder at 22.89 GFLOP, image features amortised: BASELINE.md §3).
---check: every rank also scores the FULL matrix alone and asserts the sharded + gathered matrix is bit-identical."""
+--check: every rank also scores the FULL matrix alone and asserts the sharded + gathered matrix is bit-identical.
+--check-rows K (for the full 2000 x 2000 job, where --check would double the work): rank 0 re-scores K sampled image rows
+alone and compares them bit for bit with the gathered matrix.  The all-gather is timed on its own (CUDA events, max over ranks)."""
 import argparse, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
@@ -16,6 +18,7 @@ from medical_vision_langauge_transformer_b200.modules import config as C, model 
 ap = argparse.ArgumentParser()
 ap.add_argument("--n-img", type=int, default=64); ap.add_argument("--n-cap", type=int, default=2000); ap.add_argument("--len", type=int, default=80)
 ap.add_argument("--pair-batch", type=int, default=2048); ap.add_argument("--check", action="store_true")
+ap.add_argument("--check-rows", type=int, default=0); ap.add_argument("--out", default="")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -31,12 +34,22 @@ retrieval.rank_task(model, imgs[:2 * world], caps[:64], labels[:2 * world, :64],
 torch.cuda.synchronize()
 if world > 1: dist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+timing = {}
 e0.record()
-full, metrics = retrieval.rank_task(model, imgs, caps, labels, rank, world, a.pair_batch)
+full, metrics = retrieval.rank_task(model, imgs, caps, labels, rank, world, a.pair_batch, timing=timing)
 e1.record(); torch.cuda.synchronize()
-ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+ag_us = timing["allgather_events"][0].elapsed_time(timing["allgather_events"][1]) * 1e3 if "allgather_events" in timing else 0.0
+ms = torch.tensor([e0.elapsed_time(e1), ag_us], device="cuda")
 if world > 1: dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+ag_us = ms[1].item(); ms = ms[:1]
 ok = None
+rows_ok = None
+if a.check_rows > 0:
+    g = torch.Generator().manual_seed(7)
+    rows = torch.randperm(a.n_img, generator=g)[:a.check_rows].sort().values
+    if rank == 0:
+        alone = retrieval.score_matrix(model, imgs[rows], caps, 0, 1, a.pair_batch)
+        rows_ok = bool(torch.equal(alone, full[rows.cuda()]))
 if a.check:
     alone = retrieval.score_matrix(model, imgs, caps, 0, 1, a.pair_batch)
     ok = bool(torch.equal(alone, full))
@@ -47,5 +60,9 @@ if rank == 0:
     pairs = a.n_img * a.n_cap
     print(json.dumps({"workload": f"retrieval rank {a.n_img}x{a.n_cap} L={a.len} (config 4 shape, bounded image count)", "n_gpus": world,
                       "ms": ms.item(), "pairs_per_s": pairs / ms.item() * 1e3, "bert_tflops": pairs * 22.89e9 / ms.item() / 1e9,
-                      "sharded_equals_single_rank": ok, "R@1_i2t": metrics["i2t_retrieval"]["R@1"], "pair_batch": a.pair_batch}))
+                      "sharded_equals_single_rank": ok, "sampled_rows_bit_identical": rows_ok, "sampled_rows": a.check_rows,
+                      "allgather_us": ag_us, "allgather_bytes_per_rank": timing.get("allgather_bytes_per_rank", 0),
+                      "R@1_i2t": metrics["i2t_retrieval"]["R@1"], "R@5_i2t": metrics["i2t_retrieval"]["R@5"],
+                      "R@1_t2i": metrics["t2i_retrieval"]["R@1"], "pair_batch": a.pair_batch,
+                      "pair_loop": "CUDA graph replay per pair batch"}))
 if world > 1: dist.destroy_process_group()
