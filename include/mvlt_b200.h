@@ -145,6 +145,15 @@ int mvlt_patch_merge_ln(const float* x, void* out, int out_dtype, const float* g
 int mvlt_window_attention(const void* qkv, void* out, int dtype, const float* relbias, int B, int H, int W, int C,
                           int heads, int window, int shift, float scale, mvlt_stream_t stream);
 
+/* First half of a Swin block up to the attention input in ONE tcgen05 kernel on CTA pairs (cta_group::2):
+ *   out (bf16 [B*H*W, N], rows WINDOW-MAJOR for the image rolled by -shift) = LayerNorm(x) . w^T + bias
+ * — norm1 (vfe.py:356) + torch.roll (:361) + window_partition (:363-364) + the qkv Linear (:231).  The LayerNorm prologue gathers
+ * the token rows of the natural-order fp32 residual stream x [B*H*W, C] (row stride ldx) that belong to 256 consecutive output
+ * rows and keeps them in shared memory as the A operand while the N columns are walked in 256-wide chunks.  w bf16 [N, C],
+ * bias fp32 [N] or NULL, N % 32 == 0, C in {192, 384}. */
+int mvlt_swin_ln_qkv(const float* x, long long ldx, const float* gamma, const float* beta, float eps, const void* w,
+                     const float* bias, void* out, int B, int H, int W, int C, int N, int window, int shift, mvlt_stream_t stream);
+
 /* Second half of a Swin block in ONE tcgen05 kernel on CTA pairs (cta_group::2), in place on the fp32 residual stream x [M, C]:
  *   x <- x + o . w_proj^T + b_proj (vfe.py:252, :384), then x <- x + fc2(GELU(fc1(LayerNorm(x)))) (vfe.py:385, :136-139).
  * o = window-attention output, bf16 [M, C] dense, or NULL (MLP half only; w_proj / b_proj ignored).  The new residual rows stay

@@ -279,6 +279,9 @@ class SwinTransformer(nn.Module):
         # rows stay in tensor memory between the two halves) for the widths in MVLT_BLOCK_TAIL (bf16 mode; default 192,384).
         tail_widths = tuple(int(v) for v in os.environ.get("MVLT_BLOCK_TAIL", "192,384").split(",") if v.strip()) \
             if self.precision == "bf16" else ()
+        # norm1 + roll + window_partition + qkv as ONE tcgen05 kernel on CTA pairs (csrc/ln_qkv.cu) for the widths in MVLT_LN_QKV
+        lnqkv_widths = tuple(int(v) for v in os.environ.get("MVLT_LN_QKV", "192,384").split(",") if v.strip()) \
+            if self.precision == "bf16" else ()
         taps = self.taps
         if taps is not None:
             taps["patch_embed"] = X.clone().view(B, -1, X.shape[-1])
@@ -295,6 +298,9 @@ class SwinTransformer(nn.Module):
                 if a_first is not None:
                     a, a_first = a_first, None
                     qkv = ops.linear(a, w["qkv_w"], w["qkv_b"])
+                elif win_tc and C in lnqkv_widths and C in ops.LN_QKV_WIDTHS:
+                    qkv = ops.swin_ln_qkv(X, w["n1w"], w["n1b"], blk.norm1.eps, w["qkv_w"], w["qkv_b"], B, H, W, blk.window_size,
+                                          blk.shift_size)
                 elif win_tc:
                     a = ops.layernorm_winmajor(X, w["n1w"], w["n1b"], blk.norm1.eps, B, H, W, blk.window_size, blk.shift_size)
                     qkv = ops.linear(a, w["qkv_w"], w["qkv_b"])

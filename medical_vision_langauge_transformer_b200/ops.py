@@ -176,6 +176,25 @@ def swin_mlp(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: floa
 
 
 BLOCK_TAIL_WIDTHS = (192, 384)
+LN_QKV_WIDTHS = (192, 384)
+
+
+def swin_ln_qkv(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, w: torch.Tensor, bias: Optional[torch.Tensor],
+                B: int, H: int, W: int, window: int, shift: int) -> torch.Tensor:
+    """LayerNorm(x) @ w.T + bias with the OUTPUT rows window-major for the image rolled by -shift — norm1 + roll + window_partition +
+    qkv of a Swin block in ONE kernel on CTA pairs (fp32 x [B*H*W, C] natural order, bf16 w [N, C], C in LN_QKV_WIDTHS)."""
+    lib = _lib.ensure_init()
+    M, C, ldx = _rows2d(x)
+    N = w.shape[0]
+    assert M == B * H * W and x.dtype == torch.float32 and w.dtype == torch.bfloat16 and w.shape == (N, C) and w.is_contiguous()
+    for t, n in ((gamma, C), (beta, C)) + (((bias, N),) if bias is not None else ()):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n
+    out = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
+    rc = lib.mvlt_swin_ln_qkv(x.data_ptr(), ldx, gamma.data_ptr(), beta.data_ptr(), float(eps), w.data_ptr(), _ptr(bias), out.data_ptr(),
+                              B, H, W, C, N, window, shift, _stream())
+    _lib.check(rc, f"mvlt_swin_ln_qkv(M={M},C={C},N={N})")
+    return out
+
 
 
 def swin_block_tail(x: torch.Tensor, o: Optional[torch.Tensor], wproj: Optional[torch.Tensor], bproj: Optional[torch.Tensor],

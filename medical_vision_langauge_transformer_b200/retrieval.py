@@ -138,6 +138,29 @@ def all_gather_scores(local: torch.Tensor, n_rows: int, world: int, group=None, 
     return full[:n_rows]
 
 
+def time_all_gather(local: torch.Tensor, n_rows: int, world: int, reps: int = 5, group=None) -> float:
+    """Device time of the path's one collective on its own, in microseconds: the ranks are aligned with a barrier first (inside
+    the job the interval around the all-gather also contains the wait for the slowest rank's scoring), then the all-gather of
+    the real slabs is repeated `reps` times between two CUDA events; -> max over ranks of the mean."""
+    if world == 1:
+        return 0.0
+    import torch.distributed as dist
+    dist.barrier(group=group)
+    torch.cuda.synchronize(local.device)
+    all_gather_scores(local, n_rows, world, group)                # warm (buffers, NCCL channel set-up for this size)
+    dist.barrier(group=group)
+    torch.cuda.synchronize(local.device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        all_gather_scores(local, n_rows, world, group)
+    e1.record()
+    torch.cuda.synchronize(local.device)
+    t = torch.tensor([e0.elapsed_time(e1) * 1e3 / reps], device=local.device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return t.item()
+
+
 def compute_ranks(scores, labels):
     """run_retrieval.py:220-249: per image row the position of the first matching caption in descending-score order, then
     per caption column. -> (i2t, t2i) as Python lists.  A CUDA score matrix (what `score_matrix` / `all_gather_scores`

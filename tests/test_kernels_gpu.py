@@ -332,6 +332,27 @@ def test_swin_block_tail(cuda, M, C, with_proj):
     assert torch.equal(xf, xf2), "run-to-run bit reproducibility"
 
 
+@pytest.mark.parametrize("B,H,C,shift", [(2, 14, 384, 0), (2, 14, 384, 3), (64, 14, 384, 3), (3, 28, 192, 3), (64, 28, 192, 0), (1, 14, 384, 3)])
+def test_swin_ln_qkv(cuda, B, H, C, shift):
+    """norm1 + roll + window_partition + qkv in one CTA-pair kernel against the two-kernel path (window-major LayerNorm, then the
+    tcgen05 GEMM): same bf16 A operand, same k order -> the results agree to fp32 summation order; and against torch."""
+    from medical_vision_langauge_transformer_b200 import ops
+    N = 3 * C
+    x = rnd(B * H * H, C, seed=B + H)
+    g, b = 1 + rnd(C, seed=4, scale=0.1), rnd(C, seed=5, scale=0.1)
+    w, bias = rnd(N, C, seed=6, scale=C ** -0.5).bfloat16(), rnd(N, seed=7, scale=0.1)
+    a = ops.layernorm_winmajor(x, g, b, 1e-5, B, H, H, 7, shift)
+    two = ops.linear(a, w, bias)
+    one = ops.swin_ln_qkv(x, g, b, 1e-5, w, bias, B, H, H, 7, shift)
+    assert one.shape == two.shape and one.dtype == torch.bfloat16
+    assert relerr(one, two) < 4e-3, relerr(one, two)               # one bf16 ulp where the fp32 sums differ in the last bit
+    perm = ops.window_major_index(B, H, H, 7, shift, device="cuda")
+    ref = torch.empty(B * H * H, N, device="cuda")
+    ref[perm] = F.layer_norm(x, (C,), g, b, 1e-5).bfloat16().float() @ w.float().t() + bias
+    assert relerr(one, ref) < 4e-3
+    assert torch.equal(one, ops.swin_ln_qkv(x, g, b, 1e-5, w, bias, B, H, H, 7, shift))
+
+
 @pytest.mark.parametrize("B,H,C,shift", [(2, 56, 96, 0), (2, 56, 96, 3), (3, 28, 192, 3), (2, 14, 384, 3), (5, 7, 768, 0)])
 def test_layernorm_winmajor(cuda, B, H, C, shift):
     from medical_vision_langauge_transformer_b200 import ops

@@ -26,6 +26,7 @@ def label(n, args):
     if n == "mvlt_layernorm_rows": return f"layernorm rows{args[8]} C{args[9]}"
     if n == "mvlt_window_attention": return f"window_attn H{args[5]} C{args[7]} shift{args[10]}"
     if n == "mvlt_swin_mlp_fused": return f"swin_mlp_fused M{args[9]} C{args[10]}"
+    if n == "mvlt_swin_ln_qkv": return f"swin_ln_qkv M{args[8] * args[9] * args[10]} C{args[11]} N{args[12]}"
     if n == "mvlt_swin_block_tail": return f"swin_block_tail M{args[12]} C{args[13]}"
     if n == "mvlt_window_attention_tc": return f"window_attn_tc H{args[4]} C{args[6]} shift{args[9]}"
     if n == "mvlt_layernorm_rows_winmajor": return f"layernorm_winmajor rows{args[5] * args[6] * args[7]} C{args[8]}"
