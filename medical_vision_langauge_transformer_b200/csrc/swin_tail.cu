@@ -34,7 +34,7 @@ namespace mvlt {
 constexpr int BT_THREADS = 18 * 32;        // warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-17 compute
 constexpr int BT_CW0 = 2;                  // first compute warp
 constexpr int BT_NCW = 16;
-constexpr int BT_ACC1_COL = 384;
+constexpr int BT_ACC1_COL = 384;            // ACC2 (C <= 384 columns) first, then the 128-column fc1 accumulator
 
 // Shared-memory plan.  What the first version's clock64 trace showed (profiles/r02_tail_trace_v1.log): (1) the residual chunks
 // were only requested after the proj product had retired (their buffers aliased the o tile): 8.7k cycles of exposed HBM time;
@@ -45,12 +45,14 @@ constexpr int BT_ACC1_COL = 384;
 // tiles are [64 rows, 64 k] (8 KB; C-wide outputs as 128-column sub-tiles) in a deeper ring; A2 is three 16 KB half-chunk
 // buffers instead of two 32 KB chunks; gamma / beta / biases are staged in shared memory.
 template <int C> struct TailPlan {
-  static_assert(C == 384 || C == 192, "Swin-S stage 1 / stage 2 widths");
-  static constexpr int KB1 = C / 64;                    // k-blocks of the C-wide contractions (proj, fc1)
-  static constexpr int WN = C == 384 ? 128 : 192;       // output columns per MMA of the C-wide products (proj, fc2)
+  static_assert(C == 384 || C == 192 || C == 96, "Swin-S stage 0 / 1 / 2 widths");
+  // k-blocks of the C-wide contractions (proj, fc1).  C = 96: the second k-block is half empty — TMA zero-fills the columns
+  // past C of the o tile and of the weight tiles, the LayerNorm pass writes zeros there — and all four k-steps run
+  static constexpr int KB1 = (C + 63) / 64;
+  static constexpr int WN = C == 384 ? 128 : C;         // output columns per MMA of the C-wide products (proj, fc2)
   static constexpr int NSUB = C / WN;                   // such sub-tiles per k-block
   static constexpr int WROWS = WN / 2;                  // weight rows per CTA and tile
-  static constexpr int SLOT = WROWS * 128;              // ring slot bytes (fc1 tiles: 64 rows = 8 KB, fit either way)
+  static constexpr int SLOT = (WROWS > 64 ? WROWS : 64) * 128;   // ring slot bytes (fc1 tiles are 64 rows = 8 KB)
   static constexpr int HID = 4 * C;
   static constexpr int NCHUNK = HID / 128;
   static constexpr int XCH = C / 32;                    // 32-column fp32 chunks of a residual row
@@ -342,6 +344,11 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_consta
     const float rstd = 1.0f / sqrtf(((pq.x + pq.y) + (pq.z + pq.w)) * (1.0f / (float)C) + p.eps);
     // pass 3: normalise -> bf16 -> A1 (K-major, 128-byte rows, 16-byte slots XOR (row & 7)); the o tile there is dead
     // (acc0_full), and so are the x chunks in the A2 region (every warp passed the barriers above)
+    if (XCH % 2 != 0 && part == 3) {             // C = 96: zero the unused upper half of the last k-block (columns C .. C + 31)
+      uint8_t* dst = a1 + (XCH >> 1) * 16384 + r * 128;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dst + ((((uint32_t)(4 + i)) ^ rsw) << 4)) = make_uint4(0, 0, 0, 0);
+    }
 #pragma unroll 1
     for (int c = part; c < XCH; c += 4) {
       uint32_t v[32];
@@ -517,7 +524,7 @@ extern "C" int mvlt_swin_block_tail(const void* o, float* x, long long ldx, cons
                                     long long M, int C, int hidden, cudaStream_t stream) {
   if (!x || !gamma || !beta || !w1 || !b1 || !w2 || !b2 || M <= 0) return MVLT_ERR_INVALID;
   if (o && (!w_proj || !b_proj)) return MVLT_ERR_INVALID;
-  if (hidden != 4 * C || (C != 192 && C != 384)) return MVLT_ERR_UNSUPPORTED;
+  if (hidden != 4 * C || (C != 96 && C != 192 && C != 384)) return MVLT_ERR_UNSUPPORTED;
   if (ldx < C || ldx % 4 != 0 || ((uintptr_t)x & 15) || ((uintptr_t)w1 & 15) || ((uintptr_t)w2 & 15)) return MVLT_ERR_INVALID;
   if (o && (((uintptr_t)o & 15) || ((uintptr_t)w_proj & 15) || ((uintptr_t)b_proj & 15))) return MVLT_ERR_INVALID;
   if (((uintptr_t)gamma & 15) || ((uintptr_t)beta & 15) || ((uintptr_t)b1 & 15) || ((uintptr_t)b2 & 15)) return MVLT_ERR_INVALID;
@@ -527,6 +534,7 @@ extern "C" int mvlt_swin_block_tail(const void* o, float* x, long long ldx, cons
   TailParams p;
   p.M = M; p.b_proj = b_proj; p.gamma = gamma; p.beta = beta; p.b1 = b1; p.b2 = b2; p.eps = eps; p.with_proj = o != nullptr;
   p.trace = g_tail_trace;
+  if (C == 96) return launch_swin_tail<96>(p, o, x, ldx, o ? w_proj : nullptr, w1, w2, stream);
   if (C == 384) return launch_swin_tail<384>(p, o, x, ldx, o ? w_proj : nullptr, w1, w2, stream);
   return launch_swin_tail<192>(p, o, x, ldx, o ? w_proj : nullptr, w1, w2, stream);
 }

@@ -175,7 +175,7 @@ def swin_mlp(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: floa
     return x
 
 
-BLOCK_TAIL_WIDTHS = (192, 384)
+BLOCK_TAIL_WIDTHS = (96, 192, 384)
 LN_QKV_WIDTHS = (192, 384)
 
 

@@ -23,7 +23,7 @@ def graph_time(fn, n=20):
         e0.record(st); g.replay(); e1.record(st); st.synchronize()
     return e0.elapsed_time(e1) * 1e3 / n
 
-for (M, C) in [(256, 384), (300, 384), (12544, 384), (50176, 192)]:
+for (M, C) in [(256, 96), (300, 96), (200704, 96), (12544, 384), (50176, 192)]:
     for with_proj in (True, False):
         x = rnd(M, C, seed=1); o = rnd(M, C, seed=2).bfloat16()
         wp, bp = rnd(C, C, seed=3, scale=C ** -0.5).bfloat16(), rnd(C, seed=4, scale=0.1)
