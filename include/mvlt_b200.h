@@ -163,6 +163,17 @@ int mvlt_swin_block_tail(const void* o, float* x, long long ldx, const void* w_p
                          const float* beta, float eps, const void* w1, const float* b1, const void* w2, const float* b2,
                          long long M, int C, int hidden, mvlt_stream_t stream);
 
+/* nn.Linear + residual + LayerNorm of the BERT post-LN sites in ONE tcgen05 kernel (clusters of four CTAs, see csrc/gemm_ln.cu):
+ *   y = LayerNorm(A . W^T + bias + residual) * gamma + beta
+ * — BertSelfOutput (HF modeling_bert.py:295-297: dense, dropout (eval: identity), LayerNorm(hidden + input)) and BertOutput (:352-354).
+ * A bf16 [M, K] (row stride lda), W bf16 [N, K] (nn.Linear layout), bias / gamma / beta fp32 [N], residual fp32 [M, N];
+ * y is written as fp32 to out_f32 (may alias residual) and, when out_bf16 != NULL, as bf16 to out_bf16 (the A operand of the next
+ * GEMM).  N must be 768 (MVLT_ERR_UNSUPPORTED otherwise: the caller keeps GEMM + mvlt_layernorm_rows), K % 16 == 0. */
+int mvlt_linear_residual_layernorm(const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                                   const float* residual, long long ldres, const float* gamma, const float* beta, float eps,
+                                   float* out_f32, long long ld32, void* out_bf16, long long ld16, int M, int N, int K,
+                                   mvlt_stream_t stream);
+
 /* The same attention on tcgen05 / TMEM / TMA (bf16): qkv [B*nW*49, 3C] with rows WINDOW-MAJOR for this block's shift (as
  * written by mvlt_layernorm_rows_winmajor + the qkv GEMM), out [B*H*W, C] in NATURAL token order (window_reverse + the
  * reverse roll of vfe.py:159-173, :373-381 are the output scatter).  Two windows per 128-lane accumulator tile, S = Q.K^T

@@ -11,6 +11,8 @@ the greedy / beam-search decode of `MVLBertForImageCaption` (its teacher-forced 
 """
 from __future__ import annotations
 
+import os
+
 import random
 
 import torch
@@ -189,6 +191,8 @@ class MVLBert(_PackedMixin, nn.Module):
                                        bf16_copy=bf)
         heads, eps = cfg.num_attention_heads, cfg.layer_norm_eps
         taps = self.taps
+        # MVLT_LINEAR_LN=0 keeps the unfused GEMM (reduce-add epilogue) + layernorm_rows chain (bf16 mode; fp32 mode always does)
+        fused_ln = bf and cfg.hidden_size in ops.LINEAR_LN_WIDTHS and os.environ.get("MVLT_LINEAR_LN", "1") != "0"
         if taps is not None:
             taps["image_feature"] = image_feature.clone()
             taps["embedding"] = h.clone().view(B, S, -1)
@@ -197,13 +201,20 @@ class MVLBert(_PackedMixin, nn.Module):
             ctx = ops.joint_attention(qkv, kmask, B, S, heads, bool(seq2seq_mask), n_obj + 1)
             # residual GEMMs accumulate IN PLACE into the fp32 hidden state (the tcgen05 epilogue reduce-adds its tile at the
             # L2, the residual never enters the SM); each LayerNorm then rewrites the rows it has just read
-            ops.linear(ctx, w["ao_w"], w["ao_b"], residual=h, out=h)
-            h1 = ops.layernorm(h, w["ln1_w"], w["ln1_b"], eps, torch.float32, out=h, bf16_copy=bf)
-            h1, h1b = h1 if bf else (h1, None)
-            f = ops.linear(h1b if bf else h1, w["fi_w"], w["fi_b"], act=ops.ACT_GELU)
-            ops.linear(f, w["fo_w"], w["fo_b"], residual=h1, out=h1)
-            h = ops.layernorm(h1, w["ln2_w"], w["ln2_b"], eps, torch.float32, out=h1, bf16_copy=bf)
-            h, hb = h if bf else (h, None)
+            if fused_ln:
+                # dense + residual + LayerNorm as ONE tcgen05 kernel on clusters of four CTAs (csrc/gemm_ln.cu): the fp32 rows are
+                # read once and written once per half-layer instead of GEMM read-modify-write + LayerNorm read + write
+                h1, h1b = ops.linear_residual_layernorm(ctx, w["ao_w"], w["ao_b"], h, w["ln1_w"], w["ln1_b"], eps, out=h)
+                f = ops.linear(h1b, w["fi_w"], w["fi_b"], act=ops.ACT_GELU)
+                h, hb = ops.linear_residual_layernorm(f, w["fo_w"], w["fo_b"], h1, w["ln2_w"], w["ln2_b"], eps, out=h1)
+            else:
+                ops.linear(ctx, w["ao_w"], w["ao_b"], residual=h, out=h)
+                h1 = ops.layernorm(h, w["ln1_w"], w["ln1_b"], eps, torch.float32, out=h, bf16_copy=bf)
+                h1, h1b = h1 if bf else (h1, None)
+                f = ops.linear(h1b if bf else h1, w["fi_w"], w["fi_b"], act=ops.ACT_GELU)
+                ops.linear(f, w["fo_w"], w["fo_b"], residual=h1, out=h1)
+                h = ops.layernorm(h1, w["ln2_w"], w["ln2_b"], eps, torch.float32, out=h1, bf16_copy=bf)
+                h, hb = h if bf else (h, None)
             if taps is not None and li in (0, len(pk["layers"]) - 1):
                 taps[f"bert{li}"] = h.clone().view(B, S, -1)
         return h, hb, B, S

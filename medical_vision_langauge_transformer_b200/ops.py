@@ -175,6 +175,32 @@ def swin_mlp(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: floa
     return x
 
 
+LINEAR_LN_WIDTHS = (768,)
+
+
+def linear_residual_layernorm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], residual: torch.Tensor, gamma: torch.Tensor,
+                              beta: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None, bf16_copy: bool = True):
+    """LayerNorm(a @ w.T + bias + residual) * gamma + beta in ONE kernel (bf16 a [M,K], bf16 w [N,K], fp32 residual [M,N], N in
+    LINEAR_LN_WIDTHS) — the BertSelfOutput / BertOutput pattern.  -> fp32 [M,N] (`out`, may be `residual`), or (fp32, bf16 shadow)."""
+    lib = _lib.ensure_init()
+    M, K, lda = _rows2d(a)
+    N = w.shape[0]
+    Mr, Nr, ldr = _rows2d(residual)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape == (N, K) and w.is_contiguous()
+    assert residual.dtype == torch.float32 and (Mr, Nr) == (M, N)
+    for t in (gamma, beta) + ((bias,) if bias is not None else ()):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == N
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    Mo, No, ldo = _rows2d(out)
+    assert out.dtype == torch.float32 and (Mo, No) == (M, N)
+    shadow = torch.empty((M, N), device=a.device, dtype=torch.bfloat16) if bf16_copy else None
+    rc = lib.mvlt_linear_residual_layernorm(a.data_ptr(), lda, w.data_ptr(), K, _ptr(bias), residual.data_ptr(), ldr, gamma.data_ptr(),
+                                            beta.data_ptr(), float(eps), out.data_ptr(), ldo, _ptr(shadow), N, M, N, K, _stream())
+    _lib.check(rc, f"mvlt_linear_residual_layernorm(M={M},N={N},K={K})")
+    return (out, shadow) if bf16_copy else out
+
+
 BLOCK_TAIL_WIDTHS = (96, 192, 384)
 LN_QKV_WIDTHS = (192, 384)
 

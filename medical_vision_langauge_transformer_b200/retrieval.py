@@ -173,8 +173,10 @@ def compute_ranks(scores, labels):
     return compute_ranks_host(scores, labels)
 
 
-def compute_ranks_host(scores, labels):
-    """The reference's numpy algorithm for host arrays (np.argsort reversed; ties as numpy breaks them)."""
+def compute_ranks_host(scores, labels, kind=None):
+    """The reference's numpy algorithm for host arrays (np.argsort reversed).  kind=None is the reference's call: numpy's default
+    sort is NOT stable, so where other entries tie with the best positive's score the rank it reports is implementation-defined;
+    kind="stable" fixes the order of equal scores (decreasing index after the reversal) — the rule the device kernel implements."""
     scores = np.asarray(scores.detach().cpu() if torch.is_tensor(scores) else scores)
     labels = np.asarray(labels.detach().cpu() if torch.is_tensor(labels) else labels)
     n = scores.shape[1]
@@ -182,7 +184,7 @@ def compute_ranks_host(scores, labels):
     def ranks(sim, lab):
         out = []
         for s, l in zip(sim, lab):
-            hit = np.nonzero(l[np.argsort(s)[::-1]] == 1)[0]
+            hit = np.nonzero(l[np.argsort(s, kind=kind)[::-1]] == 1)[0]
             out.append(int(hit[0]) if hit.size else n)
         return out
 

@@ -354,6 +354,39 @@ def test_swin_ln_qkv(cuda, B, H, C, shift):
     assert torch.equal(one, ops.swin_ln_qkv(x, g, b, 1e-5, w, bias, B, H, H, 7, shift))
 
 
+@pytest.mark.parametrize("M,K", [(1, 768), (77, 768), (128, 3072), (257, 768), (300, 3072), (8384, 768), (8384, 3072), (20000, 784), (70000, 768)])
+def test_linear_residual_layernorm(cuda, M, K):
+    """dense + bias + residual + LayerNorm in one cluster-of-four kernel (BertSelfOutput / BertOutput) against torch fp32 on the same
+    bf16 operands, against the two-kernel path (tcgen05 GEMM with reduce-add epilogue, then layernorm_rows), in place, ragged M
+    (row tiles of 256), a K that is not a multiple of the 64-wide k-block, several tiles per cluster (M = 70000), bit reproducible."""
+    from medical_vision_langauge_transformer_b200 import ops
+    N = 768
+    a = rnd(M, K, seed=1).bfloat16(); res = rnd(M, N, seed=2, scale=2.0) + 0.5
+    w, bias = rnd(N, K, seed=3, scale=K ** -0.5).bfloat16(), rnd(N, seed=4, scale=0.1)
+    g, b = 1 + rnd(N, seed=5, scale=0.1), rnd(N, seed=6, scale=0.1)
+    ref = F.layer_norm(a.float() @ w.float().t() + bias + res, (N,), g, b, 1e-12)
+    out, shadow = ops.linear_residual_layernorm(a, w, bias, res, g, b, 1e-12)
+    assert out.dtype == torch.float32 and shadow.dtype == torch.bfloat16 and out.shape == shadow.shape == (M, N)
+    assert relerr(out, ref) < 1e-5, relerr(out, ref)                       # fp32 accumulation-order noise only
+    assert torch.equal(shadow, out.bfloat16())                              # the shadow is the fp32 row rounded once
+    two = res.clone()
+    ops.linear(a, w, bias, residual=two, out=two)
+    two, two_b = ops.layernorm(two, g, b, 1e-12, torch.float32, out=two, bf16_copy=True)
+    assert relerr(out, two) < 1e-5
+    r2 = res.clone()                                                        # in place on the residual stream
+    o2, s2 = ops.linear_residual_layernorm(a, w, bias, r2, g, b, 1e-12, out=r2)
+    assert o2.data_ptr() == r2.data_ptr() and torch.equal(o2, out) and torch.equal(s2, shadow)
+    o3 = ops.linear_residual_layernorm(a, w, None, res, g, b, 1e-12, bf16_copy=False)   # no bias, no shadow
+    assert relerr(o3, F.layer_norm(a.float() @ w.float().t() + res, (N,), g, b, 1e-12)) < 1e-5
+
+
+def test_linear_residual_layernorm_unsupported_width(cuda):
+    from medical_vision_langauge_transformer_b200 import ops
+    a, w = rnd(64, 256).bfloat16(), rnd(512, 256).bfloat16()
+    with pytest.raises(RuntimeError):
+        ops.linear_residual_layernorm(a, w, None, rnd(64, 512), rnd(512), rnd(512), 1e-12)
+
+
 @pytest.mark.parametrize("B,H,C,shift", [(2, 56, 96, 0), (2, 56, 96, 3), (3, 28, 192, 3), (2, 14, 384, 3), (5, 7, 768, 0)])
 def test_layernorm_winmajor(cuda, B, H, C, shift):
     from medical_vision_langauge_transformer_b200 import ops

@@ -30,6 +30,7 @@ def label(n, args):
     if n == "mvlt_swin_block_tail": return f"swin_block_tail M{args[12]} C{args[13]}"
     if n == "mvlt_window_attention_tc": return f"window_attn_tc H{args[4]} C{args[6]} shift{args[9]}"
     if n == "mvlt_layernorm_rows_winmajor": return f"layernorm_winmajor rows{args[5] * args[6] * args[7]} C{args[8]}"
+    if n == "mvlt_linear_residual_layernorm": return f"linear_residual_layernorm {args[14]}x{args[15]}x{args[16]}"
     if n == "mvlt_joint_attention_tc": return f"joint_attention_tc S{args[4]}"
     return n.replace("mvlt_", "")
 def wrap(n):
