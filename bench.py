@@ -259,13 +259,14 @@ def gemm_roofline(model, x, ids, pk, steps=3):
 
 
 def fused_tensor_rooflines(model, x, ids, pk):
-    """The fused tcgen05 kernels that replaced GEMM + row-kernel chains (csrc/swin_tail.cu, csrc/ln_qkv.cu) against the measured
+    """The fused tcgen05 kernels that replaced GEMM + row-kernel chains (csrc/swin_tail.cu, csrc/ln_qkv.cu, csrc/gemm_ln.cu) against the measured
     cuBLAS bf16 peak: every launch of a family in one forward is recorded, the launches are replayed back to back as one CUDA
     graph, achieved = algorithmic FLOPs of their contractions (2*M*N*K, unpadded) / device time."""
     import torch
     from medical_vision_langauge_transformer_b200 import ops
     fams = {"swin_block_tail": lambda a, kw: 2.0 * a[0].shape[0] * a[0].shape[1] * a[0].shape[1] * (9 if a[1] is not None else 8),
-            "swin_ln_qkv": lambda a, kw: 2.0 * a[0].shape[0] * a[0].shape[1] * a[4].shape[0]}
+            "swin_ln_qkv": lambda a, kw: 2.0 * a[0].shape[0] * a[0].shape[1] * a[4].shape[0],
+            "linear_residual_layernorm": lambda a, kw: 2.0 * a[0].shape[0] * a[0].shape[1] * a[1].shape[0]}
     calls = {k: [] for k in fams}
     orig = {k: getattr(ops, k) for k in fams}
 
