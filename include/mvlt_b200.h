@@ -174,6 +174,10 @@ int mvlt_linear_residual_layernorm(const void* A, long long lda, const void* W, 
                                    float* out_f32, long long ld32, void* out_bf16, long long ld16, int M, int N, int K,
                                    mvlt_stream_t stream);
 
+/* Number of 256-row tiles mvlt_linear_residual_layernorm processes concurrently on the current device (resident clusters of four
+ * CTAs: 33 on a 148-SM B200), or a negative error code.  Host-side routing (ops.use_linear_ln) asks whether M fills a wave. */
+int mvlt_linear_ln_resident_tiles(void);
+
 /* The same attention on tcgen05 / TMEM / TMA (bf16): qkv [B*nW*49, 3C] with rows WINDOW-MAJOR for this block's shift (as
  * written by mvlt_layernorm_rows_winmajor + the qkv GEMM), out [B*H*W, C] in NATURAL token order (window_reverse + the
  * reverse roll of vfe.py:159-173, :373-381 are the output scatter).  Two windows per 128-lane accumulator tile, S = Q.K^T

@@ -25,6 +25,7 @@ PROTOTYPES = {
     "mvlt_maxpool_nhwc": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mvlt_swin_mlp_fused": [_vp, _ll, _vp, _vp, _f, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp],
     "mvlt_linear_residual_layernorm": [_vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _f, _vp, _ll, _vp, _ll, _i, _i, _i, _vp],
+    "mvlt_linear_ln_resident_tiles": [],
     "mvlt_swin_ln_qkv": [_vp, _ll, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mvlt_swin_block_tail": [_vp, _vp, _ll, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp],
     "mvlt_ln_linear_bf16": [_vp, _ll, _vp, _vp, _f, _vp, _vp, _vp, _ll, _ll, _i, _i, _i, _vp],

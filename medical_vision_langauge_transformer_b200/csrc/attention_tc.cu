@@ -508,9 +508,15 @@ joint_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const bool do_pv = pv_cnt[slot] < s_cnt[slot];
         if (!do_pv && s_cnt[slot] >= n_slot) continue;
         const uint32_t u = do_pv ? pv_cnt[slot] : s_cnt[slot];
-        const bool ready = do_pv ? (mbar_test(&p_full[slot], u & 1) && mbar_test(&v_full[slot], u & 1))
-                                 : (mbar_test(&o_empty[slot], (u & 1) ^ 1) && mbar_test(&qk_full[slot], u & 1));
-        if (!__any_sync(0xffffffffu, ready)) continue;
+        // Q.K^T of the slot's NEXT tile only overwrites the score columns, whose last reader is the P.V just issued in front of
+        // it (same thread: the tensor pipe keeps issue order) — it does not wait for the epilogue.  P.V writes the O columns
+        // and does: o_empty.
+        const bool ready = do_pv ? (mbar_test(&p_full[slot], u & 1) && mbar_test(&v_full[slot], u & 1) && mbar_test(&o_empty[slot], (u & 1) ^ 1))
+                                 : mbar_test(&qk_full[slot], u & 1);
+        if (!__any_sync(0xffffffffu, ready)) {
+          JT_STAMP(slot + (int)u * JT_SLOTS, do_pv ? 12 : 11);     // last poll that found the step not ready
+          continue;
+        }
         tc_fence_after();
         int row0, head, b0, ns;
         item_of(slot + (int)u * JT_SLOTS, row0, head, b0, ns);

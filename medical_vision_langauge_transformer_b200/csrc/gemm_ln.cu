@@ -420,6 +420,40 @@ extern "C" int mvlt_debug_gemm_ln_trace(void* dev_buf) {
   return MVLT_OK;
 }
 
+static int gemm_ln_configure() {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured)) {
+    cudaError_t e = cudaFuncSetAttribute(gl::gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gl::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (gl::g_max_clusters == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(gl::THREADS);
+    cfg.dynamicSmemBytes = gl::SMEM_BYTES;
+    cfg.gridDim = dim3(4 * 32);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, gl::gemm_ln_kernel, &cfg);
+    if (e != cudaSuccess) return (int)e;
+    if (n <= 0) return MVLT_ERR_UNSUPPORTED;
+    gl::g_max_clusters = n;
+  }
+  return MVLT_OK;
+}
+
+// How many 256-row tiles of mvlt_linear_residual_layernorm run at once on this device (clusters of four CTAs that can be
+// resident: 33 on a 148-SM B200), or a negative / CUDA error code.  Callers use it to decide whether a given M fills a wave.
+extern "C" int mvlt_linear_ln_resident_tiles(void) {
+  int rc = gemm_ln_configure();
+  return rc != MVLT_OK ? (rc > 0 ? -rc : rc) : gl::g_max_clusters;
+}
+
 // y = LayerNorm(A . W^T + bias + residual) (see the header of this file).  out_f32 may alias residual (every CTA reads its
 // residual tile before it writes the same tile); out_bf16 may be NULL.  N must be 768, K a multiple of 16.
 extern "C" int mvlt_linear_residual_layernorm(const void* A, long long lda, const void* W, long long ldw, const float* bias,
@@ -434,11 +468,7 @@ extern "C" int mvlt_linear_residual_layernorm(const void* A, long long lda, cons
     return MVLT_ERR_INVALID;
   int rc = mvlt_gemm_tc_init();
   if (rc != MVLT_OK) return rc;
-  static unsigned long long configured = 0;
-  if (first_use_on_device(configured)) {
-    cudaError_t e = cudaFuncSetAttribute(gl::gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gl::SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-  }
+  if ((rc = gemm_ln_configure()) != MVLT_OK) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(gl::THREADS);
   cfg.dynamicSmemBytes = gl::SMEM_BYTES;
@@ -451,15 +481,6 @@ extern "C" int mvlt_linear_residual_layernorm(const void* A, long long lda, cons
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  if (gl::g_max_clusters == 0) {
-    cfg.gridDim = dim3(4 * 32);
-    cfg.numAttrs = 1;
-    int n = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, gl::gemm_ln_kernel, &cfg);
-    if (e != cudaSuccess) return (int)e;
-    if (n <= 0) return MVLT_ERR_UNSUPPORTED;
-    gl::g_max_clusters = n;
-  }
   CUtensorMap ta, tw, tr, to32, to16;
   if ((rc = make_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, M, K, lda, gl::BK, gl::BM, CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != MVLT_OK) return rc;

@@ -192,7 +192,7 @@ class MVLBert(_PackedMixin, nn.Module):
         heads, eps = cfg.num_attention_heads, cfg.layer_norm_eps
         taps = self.taps
         # MVLT_LINEAR_LN=0 keeps the unfused GEMM (reduce-add epilogue) + layernorm_rows chain (bf16 mode; fp32 mode always does)
-        fused_ln = bf and cfg.hidden_size in ops.LINEAR_LN_WIDTHS and os.environ.get("MVLT_LINEAR_LN", "1") != "0"
+        fused_ln = bf and cfg.hidden_size in ops.LINEAR_LN_WIDTHS and os.environ.get("MVLT_LINEAR_LN", "1") != "0" and ops.use_linear_ln(B * S)
         if taps is not None:
             taps["image_feature"] = image_feature.clone()
             taps["embedding"] = h.clone().view(B, S, -1)

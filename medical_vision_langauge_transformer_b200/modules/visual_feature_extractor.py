@@ -298,7 +298,7 @@ class SwinTransformer(nn.Module):
                 if a_first is not None:
                     a, a_first = a_first, None
                     qkv = ops.linear(a, w["qkv_w"], w["qkv_b"])
-                elif win_tc and C in lnqkv_widths and C in ops.LN_QKV_WIDTHS:
+                elif win_tc and C in lnqkv_widths and C in ops.LN_QKV_WIDTHS and ops.use_ln_qkv(B * H * W, C):
                     qkv = ops.swin_ln_qkv(X, w["n1w"], w["n1b"], blk.norm1.eps, w["qkv_w"], w["qkv_b"], B, H, W, blk.window_size,
                                           blk.shift_size)
                 elif win_tc:
@@ -315,7 +315,7 @@ class SwinTransformer(nn.Module):
                 else:
                     o = ops.window_attention(qkv, w["relbias"], B, H, W, C, blk.num_heads, blk.window_size, blk.shift_size,
                                              blk.attn.scale)
-                if C in tail_widths and C in ops.BLOCK_TAIL_WIDTHS and w["fc1_w"].shape[0] == 4 * C:
+                if C in tail_widths and C in ops.BLOCK_TAIL_WIDTHS and w["fc1_w"].shape[0] == 4 * C and ops.use_block_tail(B * H * W, C):
                     ops.swin_block_tail(X, o, w["proj_w"], w["proj_b"], w["n2w"], w["n2b"], blk.norm2.eps, w["fc1_w"], w["fc1_b"],
                                         w["fc2_w"], w["fc2_b"])
                     if taps is not None and i < 2:

@@ -2,6 +2,7 @@
 memory and streams only; every arithmetic op below runs in libmvlt_b200.so.  No fallbacks."""
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -176,6 +177,51 @@ def swin_mlp(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: floa
 
 
 LINEAR_LN_WIDTHS = (768,)
+
+# ---- host-side routing between the one-wave fused kernels and the unfused chains --------------------------------------------
+# The CTA-pair / cluster kernels own 256 rows per pair (cluster) for the whole contraction: they win when the row count fills most
+# of a wave of the device's 74 SM pairs (33 four-CTA clusters) and lose to the finer-grained GEMM + row-kernel chain when it does
+# not (tools/fused_crossover.py, profiles/r02_fused_crossover_by_batch.log: break-even near batch 40-48 of the bench workload).
+# DEFAULT: the fused kernels always run — the forward stays a per-sample map BIT FOR BIT whatever the batch size (a slice of a
+# batch reproduces its rows exactly, sharded retrieval equals single-rank retrieval; tests/test_e2e_gpu.py pins both).
+# MVLT_ROUTING=auto picks per call by row count (faster below ~batch 40; results then depend on the batch size in the last bits).
+_ROUTE = {}
+
+
+def _route_info():
+    dev = torch.cuda.current_device()
+    if dev not in _ROUTE:
+        lib = _lib.ensure_init()
+        tiles = lib.mvlt_linear_ln_resident_tiles()
+        if tiles <= 0:
+            _lib.check(tiles if tiles < 0 else -2, "mvlt_linear_ln_resident_tiles")
+        _ROUTE[dev] = (torch.cuda.get_device_properties(dev).multi_processor_count // 2, tiles)
+    return _ROUTE[dev]
+
+
+def _fills_wave(units: int, slots: int, min_first: float, min_eff: float) -> bool:
+    if os.environ.get("MVLT_ROUTING", "fixed") != "auto":
+        return True
+    if units <= slots:
+        return units >= min_first * slots
+    waves = -(-units // slots)
+    return units / (waves * slots) >= min_eff
+
+
+def use_linear_ln(rows: int) -> bool:
+    """linear_residual_layernorm vs GEMM (reduce-add epilogue) + layernorm: measured break-even at ~0.7 of a wave of clusters."""
+    return _fills_wave(-(-rows // 256), _route_info()[1], 0.70, 0.85)
+
+
+def use_block_tail(rows: int, C: int) -> bool:
+    if C != 384:
+        return True                     # C = 192: faster than the chain at every batch measured (8..64); C = 96 is opt-in anyway
+    return _fills_wave(-(-rows // 256), _route_info()[0], 0.50, 0.85)
+
+
+def use_ln_qkv(rows: int, C: int) -> bool:
+    return _fills_wave(-(-rows // 256), _route_info()[0], 0.60, 0.90)
+
 
 
 def linear_residual_layernorm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], residual: torch.Tensor, gamma: torch.Tensor,

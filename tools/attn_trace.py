@@ -19,9 +19,9 @@ fn(None)
 t = buf.cpu().tolist()
 t0 = t[0]
 print(f"kernel body {t[1] - t0} cycles")
-names = ["qk_tma_issue", "v_tma_issue", "S_mma_issue", "PV_mma_issue", "mask_filled", "mask_bar", "s_full_seen", "pass1_done", "p_written", "o_full_seen", "epi_done"]
+names = ["qk_tma_issue", "v_tma_issue", "S_mma_issue", "PV_mma_issue", "mask_filled", "mask_bar", "s_full_seen", "pass1_done", "p_written", "o_full_seen", "epi_done", "S_last_not_ready", "PV_last_not_ready"]
 for n in range(8):
-    row = t[16 + n * 16: 16 + n * 16 + 11]
+    row = t[16 + n * 16: 16 + n * 16 + 13]
     if not any(row):
         continue
     print(f"tile {n} (slot {n % 2}): " + "  ".join(f"{nm} {v - t0 if v else -1}" for nm, v in zip(names, row)))
