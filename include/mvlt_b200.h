@@ -249,6 +249,33 @@ int mvlt_masked_ce_rows(const float* logits, long long ld, const long long* labe
 int mvlt_rank_first_positive(const float* scores, long long lds, const unsigned char* labels, long long ldl,
                              int* row_ranks, int* col_ranks, int R, int C, mvlt_stream_t stream);
 
+/* ---- first slice of the training step: the non-GEMM kernels of the backward of ONE BertLayer
+ * (HF modeling_bert.py:359-421 under run_pretrain.py:177-184 `loss.backward()`).  dgrad / wgrad themselves are mvlt_gemm_bf16_tc
+ * calls on transposed bf16 operands (host: medical_vision_langauge_transformer_b200/training.py). ---- */
+
+/* out[c, r] = bf16(in[r, c]) for r < rows, 0 for rows <= r < ld_out: the M-contiguous operands of the wgrad GEMMs (ld_out a
+ * multiple of 8 makes the rows TMA-aligned).  in: fp32 or bf16 [rows, cols], row stride ld_in. */
+int mvlt_transpose_to_bf16(const void* in, int in_dtype, long long ld_in, void* out, long long ld_out, long long rows, int cols,
+                           mvlt_stream_t stream);
+
+/* torch.nn.functional.layer_norm backward over dense fp32 rows: x is the PRE-normalisation input, dx fp32 (+ optional bf16
+ * copy), dgamma = sum_rows dy * xhat, dbeta = sum_rows dy, reduced in a fixed order.  C % 128 == 0, C <= 1024. */
+long long mvlt_layernorm_bwd_workspace_bytes(long long rows, int C);
+int mvlt_layernorm_bwd_rows(const float* dy, const float* x, const float* gamma, float eps, float* dx, void* dx_bf16,
+                            float* dgamma, float* dbeta, void* workspace, long long rows, int C, mvlt_stream_t stream);
+
+/* out[c] = sum_r x[r, c] (bias gradients); x fp32 or bf16, fixed summation order. */
+long long mvlt_colsum_workspace_bytes(long long rows, int cols);
+int mvlt_colsum(const void* x, int dtype, long long ld, float* out, void* workspace, long long rows, int cols, mvlt_stream_t stream);
+
+/* du = df * d/du erf-GELU(u) (HF:330-342 BertIntermediate), bf16 in / out, n % 4 == 0. */
+int mvlt_gelu_bwd(const void* u, const void* df, void* du, long long n, mvlt_stream_t stream);
+
+/* dqkv (bf16 [B*S, 3C] = dq | dk | dv) of mvlt_joint_attention given dctx (bf16 [B*S, C]); probabilities are recomputed from qkv
+ * and the masks (same mask arguments as the forward).  head_dim 64, S <= 160. */
+int mvlt_joint_attention_bwd(const void* qkv, const float* kmask, const void* dctx, void* dqkv, int B, int S, int heads,
+                             int head_dim, int seq2seq, int obj_end, float scale, mvlt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

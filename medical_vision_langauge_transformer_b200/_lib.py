@@ -26,6 +26,13 @@ PROTOTYPES = {
     "mvlt_swin_mlp_fused": [_vp, _ll, _vp, _vp, _f, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp],
     "mvlt_linear_residual_layernorm": [_vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _f, _vp, _ll, _vp, _ll, _i, _i, _i, _vp],
     "mvlt_linear_ln_resident_tiles": [],
+    "mvlt_transpose_to_bf16": [_vp, _i, _ll, _vp, _ll, _ll, _i, _vp],
+    "mvlt_layernorm_bwd_workspace_bytes": [_ll, _i],
+    "mvlt_layernorm_bwd_rows": [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp],
+    "mvlt_colsum_workspace_bytes": [_ll, _i],
+    "mvlt_colsum": [_vp, _i, _ll, _vp, _vp, _ll, _i, _vp],
+    "mvlt_gelu_bwd": [_vp, _vp, _vp, _ll, _vp],
+    "mvlt_joint_attention_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp],
     "mvlt_swin_ln_qkv": [_vp, _ll, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mvlt_swin_block_tail": [_vp, _vp, _ll, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp],
     "mvlt_ln_linear_bf16": [_vp, _ll, _vp, _vp, _f, _vp, _vp, _vp, _ll, _ll, _i, _i, _i, _vp],
@@ -73,8 +80,9 @@ def load() -> C.CDLL:
                 fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
                 fn.argtypes = argtypes
                 fn.restype = C.c_int
-            lib.mvlt_mlm_ce_workspace_bytes.argtypes = [_ll, _i]
-            lib.mvlt_mlm_ce_workspace_bytes.restype = C.c_longlong
+            for name in ("mvlt_mlm_ce_workspace_bytes", "mvlt_layernorm_bwd_workspace_bytes", "mvlt_colsum_workspace_bytes"):
+                getattr(lib, name).argtypes = [_ll, _i]
+                getattr(lib, name).restype = C.c_longlong
             _lib = lib
     return _lib
 

@@ -620,3 +620,65 @@ def rank_first_positive(scores: torch.Tensor, labels: torch.Tensor):
                                       R, C, _stream())
     _lib.check(rc, "mvlt_rank_first_positive")
     return rows, cols
+
+
+# ---- backward slice (SURVEY §8 f-2, csrc/backward.cu) ------------------------------------------------------------------------
+def transpose_to_bf16(x: torch.Tensor, pad_to: int = 64) -> torch.Tensor:
+    """[rows, cols] fp32 | bf16 -> bf16 [cols, rows rounded up to `pad_to`], zero padded: an M-contiguous wgrad operand."""
+    lib = _lib.ensure_init()
+    rows, cols, ld = _rows2d(x)
+    ldo = -(-rows // pad_to) * pad_to
+    out = torch.empty((cols, ldo), device=x.device, dtype=torch.bfloat16)
+    rc = lib.mvlt_transpose_to_bf16(x.data_ptr(), _code(x), ld, out.data_ptr(), ldo, rows, cols, _stream())
+    _lib.check(rc, "mvlt_transpose_to_bf16")
+    return out
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, eps: float, bf16_copy: bool = True):
+    """Backward of layer_norm(x) * gamma + beta for dense fp32 rows -> (dx fp32, dx bf16 | None, dgamma, dbeta)."""
+    lib = _lib.ensure_init()
+    rows, C, ld = _rows2d(x)
+    assert dy.shape == x.shape and dy.dtype == x.dtype == torch.float32 and dy.is_contiguous() and x.is_contiguous() and ld == C
+    dx = torch.empty_like(x)
+    dxb = torch.empty((rows, C), device=x.device, dtype=torch.bfloat16) if bf16_copy else None
+    dg, db = torch.empty(C, device=x.device), torch.empty(C, device=x.device)
+    ws = torch.empty(max(lib.mvlt_layernorm_bwd_workspace_bytes(rows, C), 16), device=x.device, dtype=torch.uint8)
+    rc = lib.mvlt_layernorm_bwd_rows(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), float(eps), dx.data_ptr(), _ptr(dxb), dg.data_ptr(),
+                                     db.data_ptr(), ws.data_ptr(), rows, C, _stream())
+    _lib.check(rc, f"mvlt_layernorm_bwd_rows(rows={rows},C={C})")
+    return dx, dxb, dg, db
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """Column sums of [rows, cols] (fp32 | bf16) -> fp32 [cols], fixed order."""
+    lib = _lib.ensure_init()
+    rows, cols, ld = _rows2d(x)
+    out = torch.empty(cols, device=x.device)
+    ws = torch.empty(max(lib.mvlt_colsum_workspace_bytes(rows, cols), 16), device=x.device, dtype=torch.uint8)
+    rc = lib.mvlt_colsum(x.data_ptr(), _code(x), ld, out.data_ptr(), ws.data_ptr(), rows, cols, _stream())
+    _lib.check(rc, "mvlt_colsum")
+    return out
+
+
+def gelu_bwd(u: torch.Tensor, df: torch.Tensor) -> torch.Tensor:
+    """df * gelu'(u) (erf GELU), bf16 dense tensors of equal shape."""
+    lib = _lib.ensure_init()
+    assert u.shape == df.shape and u.dtype == df.dtype == torch.bfloat16 and u.is_contiguous() and df.is_contiguous()
+    du = torch.empty_like(u)
+    rc = lib.mvlt_gelu_bwd(u.data_ptr(), df.data_ptr(), du.data_ptr(), u.numel(), _stream())
+    _lib.check(rc, "mvlt_gelu_bwd")
+    return du
+
+
+def joint_attention_bwd(qkv: torch.Tensor, kmask: Optional[torch.Tensor], dctx: torch.Tensor, B: int, S: int, heads: int, seq2seq: bool,
+                        obj_end: int) -> torch.Tensor:
+    """dqkv of joint_attention(qkv, kmask, ...) given dctx; bf16 [B*S, 3C] / [B*S, C] dense, head_dim 64."""
+    lib = _lib.ensure_init()
+    M, C3, ld = _rows2d(qkv)
+    C = C3 // 3
+    assert M == B * S and ld == C3 and qkv.dtype == dctx.dtype == torch.bfloat16 and dctx.shape == (M, C) and dctx.is_contiguous()
+    dqkv = torch.empty_like(qkv)
+    rc = lib.mvlt_joint_attention_bwd(qkv.data_ptr(), _ptr(kmask), dctx.data_ptr(), dqkv.data_ptr(), B, S, heads, C // heads, int(seq2seq),
+                                      obj_end, float((C // heads) ** -0.5), _stream())
+    _lib.check(rc, f"mvlt_joint_attention_bwd(B={B},S={S})")
+    return dqkv
