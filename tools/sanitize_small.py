@@ -20,4 +20,14 @@ with torch.no_grad():
     print("pretrain", pm(x, masked.cuda(), labels.cuda(), torch.tensor([1, 0]).cuda()).item())
     cm = M.MVLBertForImageCaption(C.offline_config("caption", max_length=4)).eval(); synth.load_synth(cm, 0, "stress"); cm = cm.cuda()
     print("greedy", cm(x, None, 1, "unilm")[0].tolist())
+    # first slice of the training step: one BertLayer forward-with-saved-activations + backward (csrc/backward.cu)
+    from medical_vision_langauge_transformer_b200 import training
+with torch.no_grad():
+    vm = M.MVLBertForVQA(C.offline_config("vqa", max_length=80)).eval()
+    w = training.pack_layer(synth.load_synth(vm, 0, "stress"), "MVLBert.encoder.layer.0.")
+    h = torch.randn(2 * 131, 768, device="cuda")
+    for s2s in (False, True):
+        out, saved = training.bert_layer_forward(w, h, None, 2, 131, 12, s2s, 50)
+        dh, grads = training.bert_layer_backward(w, saved, torch.randn_like(h) * 0.1)
+        print("backward", s2s, dh.abs().max().item(), len(grads))
 torch.cuda.synchronize()
