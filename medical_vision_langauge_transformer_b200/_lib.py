@@ -27,9 +27,7 @@ PROTOTYPES = {
     "mvlt_linear_residual_layernorm": [_vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _f, _vp, _ll, _vp, _ll, _i, _i, _i, _vp],
     "mvlt_linear_ln_resident_tiles": [],
     "mvlt_transpose_to_bf16": [_vp, _i, _ll, _vp, _ll, _ll, _i, _vp],
-    "mvlt_layernorm_bwd_workspace_bytes": [_ll, _i],
     "mvlt_layernorm_bwd_rows": [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp],
-    "mvlt_colsum_workspace_bytes": [_ll, _i],
     "mvlt_colsum": [_vp, _i, _ll, _vp, _vp, _ll, _i, _vp],
     "mvlt_gelu_bwd": [_vp, _vp, _vp, _ll, _vp],
     "mvlt_joint_attention_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp],
@@ -58,6 +56,7 @@ PROTOTYPES = {
 _lib = None
 _lock = threading.Lock()
 _initialised = False
+SIZE_QUERIES = ("mvlt_mlm_ce_workspace_bytes", "mvlt_layernorm_bwd_workspace_bytes", "mvlt_colsum_workspace_bytes")
 
 
 class MvltNativeError(RuntimeError):
@@ -80,7 +79,7 @@ def load() -> C.CDLL:
                 fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
                 fn.argtypes = argtypes
                 fn.restype = C.c_int
-            for name in ("mvlt_mlm_ce_workspace_bytes", "mvlt_layernorm_bwd_workspace_bytes", "mvlt_colsum_workspace_bytes"):
+            for name in SIZE_QUERIES:                   # long long f(long long rows, int cols): workspace sizes
                 getattr(lib, name).argtypes = [_ll, _i]
                 getattr(lib, name).restype = C.c_longlong
             _lib = lib

@@ -22,6 +22,9 @@ def test_cabi_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/mvlt_b200.h but not exported"
     assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    sizes = set(re.findall(r"^long long (mvlt_\w+)\(", header, flags=re.M))
+    assert sizes == set(_lib.SIZE_QUERIES) and all(hasattr(lib, n) for n in sizes)
+    declared |= sizes
     assert lib.mvlt_abi_version() == 1
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (mvlt_\w+)", out))
