@@ -11,7 +11,7 @@ and ONE all-gather of the fp32 score slabs (torch.distributed / NCCL over NVLink
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Iterator, Optional, Tuple
 
 import numpy as np
 import torch
@@ -26,11 +26,58 @@ def shard_rows(n: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, min(lo + per, n)
 
 
+def device_chunks(host: torch.Tensor, chunk: int, device) -> Iterator[torch.Tensor]:
+    """Yields `host[i:i+chunk]` on `device`, the copy of chunk i+1 overlapping the consumer's work on chunk i: two pinned staging
+    buffers and two device buffers, H2D on a private copy stream, events both ways.  A device tensor is sliced as is.  Replaces the
+    per-batch `img.cuda()` of pageable loader output (run_retrieval.py:200-201)."""
+    n = host.shape[0]
+    if host.is_cuda:
+        for i in range(0, n, chunk):
+            yield host[i:i + chunk]
+        return
+    dev = torch.device(device)
+    copy, main = torch.cuda.Stream(device=dev), torch.cuda.current_stream(dev)
+    shape = (min(chunk, n),) + tuple(host.shape[1:])
+    pinned = [host.new_empty(shape).pin_memory() for _ in range(2)] if not host.is_pinned() else None
+    dbuf = [torch.empty(shape, device=dev, dtype=host.dtype) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    staged = [torch.cuda.Event() for _ in range(2)]
+
+    def issue(k: int):
+        lo, b = k * chunk, k % 2
+        m = min(chunk, n - lo)
+        with torch.cuda.stream(copy):
+            if k >= 2:
+                copy.wait_event(consumed[b])                 # the consumer has finished with the device buffer
+            src = host[lo:lo + m]
+            if pinned is not None:
+                if k >= 2:
+                    staged[b].synchronize()                  # the previous H2D out of this staging buffer has completed
+                pinned[b][:m].copy_(src)                     # pageable -> pinned on the host
+                src = pinned[b][:m]
+            dbuf[b][:m].copy_(src, non_blocking=True)
+            staged[b].record(copy)
+            ready[b].record(copy)
+
+    chunks = -(-n // chunk)
+    if chunks:
+        issue(0)
+    for k in range(chunks):
+        if k + 1 < chunks:
+            issue(k + 1)
+        b = k % 2
+        main.wait_event(ready[b])
+        yield dbuf[b][:min(chunk, n - k * chunk)]
+        consumed[b].record(main)
+
+
 @torch.no_grad()
 def image_features(model, images: torch.Tensor, chunk: int = 64) -> torch.Tensor:
-    """Conv_layer over `images` ([n,3,224,224], host or device) -> [n,49,768] in the activation dtype."""
+    """Conv_layer over `images` ([n,3,224,224], host or device) -> [n,49,768] in the activation dtype.  Host images stream through
+    `device_chunks` (pinned, double-buffered: the copy of the next chunk overlaps the trunk of this one)."""
     dev = next(model.parameters()).device
-    outs = [model.conv(images[i:i + chunk].to(dev, non_blocking=True)) for i in range(0, images.shape[0], chunk)]
+    outs = [model.conv(x) for x in device_chunks(images, chunk, dev)]
     return torch.cat(outs) if len(outs) > 1 else outs[0]
 
 
@@ -198,6 +245,55 @@ def evaluate(scores, labels, ks=(1, 5, 10)) -> dict:
     if t2i:
         res["t2i_retrieval"] = {f"R@{k}": sum(r < k for r in t2i) / len(t2i) for k in ks}
     return res
+
+
+def pretokenize(dataset) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The reference's test split (run_retrieval.py:126-145) enumerates N^2 (image i, caption j) pairs and converts caption j's tokens
+    to ids inside `__getitem__`, i.e. N times per caption, after unpickling / indexing the image N times per image.  Here every
+    image is read once and every caption tokenised once:
+        images  float32 [N,3,224,224] (pinned when CUDA is available),
+        caption ids int64 [N, max_caption_len] (truncated / zero-padded exactly as :141-144),
+        labels  int64 [N,N]: 1 where i == j or the two entries share a cap_id (:137-139).
+    `dataset` is duck-typed on the reference's RetrievalDataset: img_num, get_data_by_idx(i) -> (image, caption, tokens, img_id,
+    cap_id), tokenizer.convert_tokens_to_ids, max_caption_len."""
+    n, L = int(dataset.img_num), int(dataset.max_caption_len)
+    ids = torch.zeros(n, L, dtype=torch.int64)
+    images, cap_ids = None, []
+    for i in range(n):
+        im, _, tokens, _, cap_id = dataset.get_data_by_idx(i)
+        im = torch.as_tensor(np.asarray(im), dtype=torch.float32)
+        if images is None:
+            images = torch.empty((n,) + tuple(im.shape), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+        images[i] = im
+        t = dataset.tokenizer.convert_tokens_to_ids(tokens)[:L]
+        ids[i, :len(t)] = torch.as_tensor(t, dtype=torch.int64)
+        cap_ids.append(cap_id)
+    uniq = {c: k for k, c in enumerate(dict.fromkeys(cap_ids))}
+    code = torch.tensor([uniq[c] for c in cap_ids])
+    labels = ((code[:, None] == code[None, :]) | torch.eye(n, dtype=torch.bool)).to(torch.int64)
+    return images, ids, labels
+
+
+def testRetrieval(model, test_data, output_file: Optional[str] = None, rank: int = 0, world: int = 1, pair_batch: int = 2048,
+                  group=None):
+    """Drop-in for run_retrieval.py:192-217: scores all N^2 pairs and returns (and, like the reference, torch.save's) `[results,
+    labels]` — two dicts keyed by the flat pair index i * N + j holding Python floats / ints, the input format of the reference's
+    `compute_ranks(dataset, results)` / `evaluate`.  `test_data` is the reference's test-split dataset (or a DataLoader around it);
+    the N^2-element loader is never iterated: inputs go through `pretokenize` + `rank_task` (trunk once per image, pinned
+    double-buffered H2D, row-sharded over `world` ranks, one all-gather) and the dicts are built from one D2H copy instead of one
+    `.item()` per pair (:205-209).  Every rank returns the dicts; rank 0 writes the file."""
+    dataset = getattr(test_data, "dataset", test_data)
+    images, ids, labels = pretokenize(dataset)
+    was_training = model.training
+    model.eval()
+    scores, _ = rank_task(model, images, ids, labels, rank, world, pair_batch, group)
+    flat = scores.reshape(-1).cpu().tolist()
+    results = dict(enumerate(flat))
+    labs = dict(enumerate(labels.reshape(-1).tolist()))
+    if output_file and rank == 0:
+        torch.save([results, labs], output_file)
+    model.train(was_training)
+    return results, labs
 
 
 def rank_task(model, images: torch.Tensor, captions: torch.Tensor, labels, rank: int = 0, world: int = 1,

@@ -342,3 +342,53 @@ def test_dropin_reference_scripts_import_and_build_with_module_aliases():
             assert mine == sig, (name, mine, sig)
         else:
             assert mine[:len(sig)] == sig, (name, mine, sig)      # same names / defaults; extra trailing kwargs are allowed
+
+
+class _FakeTokenizer:
+    eos_token = "[END]"
+
+    def convert_tokens_to_ids(self, tokens):
+        return [1000 + (sum(map(ord, t)) % 20000) for t in tokens]
+
+
+class _FakeRetrievalDataset:
+    """The fields of the reference's RetrievalDataset (run_retrieval.py:25-77) that the test split touches."""
+
+    def __init__(self, n=7, max_caption_len=12):
+        g = torch.Generator().manual_seed(4)
+        self.img_num, self.max_caption_len, self.tokenizer, self.split = n, max_caption_len, _FakeTokenizer(), "test"
+        self.images = torch.randn(n, 3, 8, 8, generator=g).numpy()
+        lens = [3, 12, 20, 1, 7, 12, 5][:n]
+        self.tokens = [[f"w{i}_{k}" for k in range(l)] + ["[END]"] for i, l in enumerate(lens)]
+        self.cap_ids = [10, 11, 12, 10, 14, 15, 12][:n]              # duplicates: different images sharing a caption id
+
+    def get_data_by_idx(self, i):
+        return self.images[i], "caption", self.tokens[i], f"img{i}", self.cap_ids[i]
+
+    def __len__(self):
+        return self.img_num ** 2
+
+    def __getitem__(self, index):                                   # restatement of run_retrieval.py:126-145 (test split)
+        img_idx, cap_idx = index // self.img_num, index % self.img_num
+        img1, _, _, _, cap_id1 = self.get_data_by_idx(img_idx)
+        _, _, tok2, _, cap_id2 = self.get_data_by_idx(cap_idx)
+        label = 1 if img_idx == cap_idx or cap_id1 == cap_id2 else 0
+        cap = np.array(self.tokenizer.convert_tokens_to_ids(tok2), dtype=np.int64)
+        new = np.zeros(self.max_caption_len, dtype=np.int64)
+        new[:min(cap.shape[0], self.max_caption_len)] = cap[:min(cap.shape[0], self.max_caption_len)]
+        return img1, new, label
+
+
+def test_pretokenize_matches_the_reference_pair_enumeration():
+    """retrieval.pretokenize reads every image and tokenises every caption ONCE; the N^2 (image, ids, label) triples the reference's
+    test split would have produced one by one (run_retrieval.py:126-145) are exactly images[i], ids[j], labels[i, j]."""
+    from medical_vision_langauge_transformer_b200 import retrieval
+    ds = _FakeRetrievalDataset()
+    images, ids, labels = retrieval.pretokenize(ds)
+    n = ds.img_num
+    assert images.shape == (n, 3, 8, 8) and ids.shape == (n, ds.max_caption_len) and ids.dtype == torch.int64 and labels.shape == (n, n)
+    for index in range(len(ds)):
+        img, cap, lab = ds[index]
+        i, j = divmod(index, n)
+        assert np.array_equal(images[i].numpy(), img) and np.array_equal(ids[j].numpy(), cap) and labels[i, j].item() == lab
+    assert labels[0, 3] == 1 and labels[2, 6] == 1 and labels[0, 1] == 0      # shared cap_id pairs are positives
