@@ -150,7 +150,7 @@ int mvlt_window_attention(const void* qkv, void* out, int dtype, const float* re
  * — norm1 (vfe.py:356) + torch.roll (:361) + window_partition (:363-364) + the qkv Linear (:231).  The LayerNorm prologue gathers
  * the token rows of the natural-order fp32 residual stream x [B*H*W, C] (row stride ldx) that belong to 256 consecutive output
  * rows and keeps them in shared memory as the A operand while the N columns are walked in 256-wide chunks.  w bf16 [N, C],
- * bias fp32 [N] or NULL, N % 32 == 0, C in {192, 384}. */
+ * bias fp32 [N] or NULL, N % 32 == 0, C in {96, 192, 384}. */
 int mvlt_swin_ln_qkv(const float* x, long long ldx, const float* gamma, const float* beta, float eps, const void* w,
                      const float* bias, void* out, int B, int H, int W, int C, int N, int window, int shift, mvlt_stream_t stream);
 

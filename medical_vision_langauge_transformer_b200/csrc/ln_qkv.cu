@@ -26,8 +26,8 @@ constexpr int LQ_NCW = 16;
 constexpr int LQ_SLOT = 128 * 128;         // one CTA's half of a [256, 64] weight tile
 
 template <int C> struct LnQkvPlan {
-  static_assert(C == 384 || C == 192, "Swin-S stage 1 / stage 2 widths");
-  static constexpr int KB1 = C / 64;
+  static_assert(C == 384 || C == 192 || C == 96, "Swin-S stage 0 / 1 / 2 widths");
+  static constexpr int KB1 = (C + 63) / 64;   // C = 96: the second k-block is half empty (zero A columns, zero-filled weight columns)
   static constexpr int A1_BYTES = KB1 * 16384;
   static constexpr int STAGING_BYTES = LQ_NCW * 2048;
   static constexpr int PAR_BYTES = 2 * C * 4;
@@ -231,9 +231,10 @@ swin_ln_qkv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
           const int c = (lane + 32 * i) * 4;
-          if (c >= C) continue;
-          const float4 g = *reinterpret_cast<const float4*>(par + c);
-          const float4 b = *reinterpret_cast<const float4*>(par + C + c);
+          if (c >= KB1 * 64) continue;
+          const bool pad = c >= C;                 // columns C .. 64 KB1 of the last k-block (C = 96): zeros, the MMAs read them
+          const float4 g = pad ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(par + c);
+          const float4 b = pad ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(par + C + c);
           const int kb = c >> 6, within = c & 63;
 #pragma unroll
           for (int u = 0; u < RU; ++u) {
@@ -244,7 +245,7 @@ swin_ln_qkv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             const float o3 = (v[u][i].w - mean[u]) * rstd[u] * g.w + b.w;
             const uint32_t off = (uint32_t)kb * 16384u + (uint32_t)r * 128u +
                                  ((((uint32_t)(within >> 3)) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)within & 4u) << 1);
-            *reinterpret_cast<uint2*>(a1 + off) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+            *reinterpret_cast<uint2*>(a1 + off) = pad ? make_uint2(0u, 0u) : make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
           }
         }
       }
@@ -353,13 +354,13 @@ extern "C" int mvlt_debug_lnqkv_trace(void* dev_buf) {
 
 // qkv (bf16 [B*H*W, N], rows WINDOW-MAJOR for the image rolled by -shift, dense) = LayerNorm(x) . w^T + bias in one kernel.
 // x: fp32 [B*H*W, C] natural token order (row stride ldx); w: bf16 [N, C] (nn.Linear layout), bias fp32 [N] or NULL; N % 32 == 0.
-// C in {192, 384}.  Replaces vfe.py:356 + :361-364 + :231 (norm1, roll, window_partition, qkv) of one SwinTransformerBlock; the
+// C in {96, 192, 384}.  Replaces vfe.py:356 + :361-364 + :231 (norm1, roll, window_partition, qkv) of one SwinTransformerBlock; the
 // output is what mvlt_window_attention_tc reads.
 extern "C" int mvlt_swin_ln_qkv(const float* x, long long ldx, const float* gamma, const float* beta, float eps, const void* w,
                                 const float* bias, void* out, int B, int H, int W, int C, int N, int window, int shift,
                                 cudaStream_t stream) {
   if (!x || !gamma || !beta || !w || !out || B <= 0 || H <= 0 || W <= 0 || N <= 0) return MVLT_ERR_INVALID;
-  if ((C != 192 && C != 384) || N % 32 != 0) return MVLT_ERR_UNSUPPORTED;
+  if ((C != 96 && C != 192 && C != 384) || N % 32 != 0) return MVLT_ERR_UNSUPPORTED;
   if (window != LQ_WS) return MVLT_ERR_UNSUPPORTED;
   if (H % window || W % window || shift < 0 || shift >= window) return MVLT_ERR_INVALID;
   if (ldx < C || ldx % 4 != 0) return MVLT_ERR_INVALID;
@@ -376,5 +377,5 @@ extern "C" int mvlt_swin_ln_qkv(const float* x, long long ldx, const float* gamm
   p.nW_shift = log2_exact(p.nW); p.nWw_shift = log2_exact(p.nWw);
   if (p.nW_shift < 0 || p.nWw_shift < 0) p.nW_shift = p.nWw_shift = -1;
   p.trace = g_lnqkv_trace;
-  return C == 384 ? launch_ln_qkv<384>(p, w, out, stream) : launch_ln_qkv<192>(p, w, out, stream);
+  return C == 384 ? launch_ln_qkv<384>(p, w, out, stream) : (C == 192 ? launch_ln_qkv<192>(p, w, out, stream) : launch_ln_qkv<96>(p, w, out, stream));
 }

@@ -248,7 +248,7 @@ def linear_residual_layernorm(a: torch.Tensor, w: torch.Tensor, bias: Optional[t
 
 
 BLOCK_TAIL_WIDTHS = (96, 192, 384)
-LN_QKV_WIDTHS = (192, 384)
+LN_QKV_WIDTHS = (96, 192, 384)
 
 
 def swin_ln_qkv(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, w: torch.Tensor, bias: Optional[torch.Tensor],

@@ -333,7 +333,8 @@ def test_swin_block_tail(cuda, M, C, with_proj):
     assert torch.equal(xf, xf2), "run-to-run bit reproducibility"
 
 
-@pytest.mark.parametrize("B,H,C,shift", [(2, 14, 384, 0), (2, 14, 384, 3), (64, 14, 384, 3), (3, 28, 192, 3), (64, 28, 192, 0), (1, 14, 384, 3)])
+@pytest.mark.parametrize("B,H,C,shift", [(2, 14, 384, 0), (2, 14, 384, 3), (64, 14, 384, 3), (3, 28, 192, 3), (64, 28, 192, 0), (1, 14, 384, 3),
+                                           (1, 56, 96, 0), (2, 56, 96, 3), (64, 56, 96, 3)])
 def test_swin_ln_qkv(cuda, B, H, C, shift):
     """norm1 + roll + window_partition + qkv in one CTA-pair kernel against the two-kernel path (window-major LayerNorm, then the
     tcgen05 GEMM): same bf16 A operand, same k order -> the results agree to fp32 summation order; and against torch."""
