@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libmvlt_b200.so")
-SOURCES = ["c_abi.cu", "gemm_tc.cu", "gemm_simt.cu", "rowwise.cu", "attention.cu", "attention_tc.cu", "heads.cu", "swin_mlp.cu", "swin_tail.cu", "ln_qkv.cu", "gemm_ln.cu", "backward.cu", "conv.cu"]
+SOURCES = ["c_abi.cu", "gemm_tc.cu", "gemm_simt.cu", "rowwise.cu", "attention.cu", "attention_tc.cu", "heads.cu", "swin_mlp.cu", "swin_tail.cu", "swin_tail96.cu", "ln_qkv.cu", "gemm_ln.cu", "backward.cu", "conv.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -22,6 +22,7 @@
 // read and three launches per block.  with_proj = 0 drops steps 1-2's product (x <- x + MLP(LN(x)) only).
 // C = 384 (stage 2: 49 row pairs of the batch-64 step) and C = 192 (stage 1).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "cg2.cuh"
@@ -505,6 +506,10 @@ static int launch_swin_tail(const TailParams& p, const void* o, float* x, long l
   return e == cudaSuccess ? MVLT_OK : (int)e;
 }
 
+// the persistent stage-0 variant (swin_tail96.cu)
+int launch_swin_tail96(const void* o, float* x, long long ldx, const void* w_proj, const float* b_proj, const float* gamma, const float* beta,
+                       float eps, const void* w1, const float* b1, const void* w2, const float* b2, long long M, cudaStream_t stream);
+
 }  // namespace mvlt
 
 using namespace mvlt;
@@ -534,7 +539,13 @@ extern "C" int mvlt_swin_block_tail(const void* o, float* x, long long ldx, cons
   TailParams p;
   p.M = M; p.b_proj = b_proj; p.gamma = gamma; p.beta = beta; p.b1 = b1; p.b2 = b2; p.eps = eps; p.with_proj = o != nullptr;
   p.trace = g_tail_trace;
-  if (C == 96) return launch_swin_tail<96>(p, o, x, ldx, o ? w_proj : nullptr, w1, w2, stream);
+  if (C == 96) {
+    // stage 0: the persistent two-tiles-in-flight kernel (swin_tail96.cu); MVLT_TAIL96=0 keeps the one-tile-per-pair kernel
+    static int persistent = -1;
+    if (persistent < 0) { const char* e = getenv("MVLT_TAIL96"); persistent = (e && atoi(e) == 0) ? 0 : 1; }
+    if (persistent) return launch_swin_tail96(o, x, ldx, w_proj, b_proj, gamma, beta, eps, w1, b1, w2, b2, M, stream);
+    return launch_swin_tail<96>(p, o, x, ldx, o ? w_proj : nullptr, w1, w2, stream);
+  }
   if (C == 384) return launch_swin_tail<384>(p, o, x, ldx, o ? w_proj : nullptr, w1, w2, stream);
   return launch_swin_tail<192>(p, o, x, ldx, o ? w_proj : nullptr, w1, w2, stream);
 }

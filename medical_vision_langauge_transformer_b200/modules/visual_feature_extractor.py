@@ -276,8 +276,9 @@ class SwinTransformer(nn.Module):
         ln_lin_widths = tuple(int(v) for v in os.environ.get("MVLT_FUSED_LN_LINEAR", "").split(",") if v.strip()) \
             if self.precision == "bf16" else ()
         # proj + residual + LN2 + fc1 + GELU + fc2 + residual as ONE tcgen05 kernel on CTA pairs (csrc/swin_tail.cu; the new residual
-        # rows stay in tensor memory between the two halves) for the widths in MVLT_BLOCK_TAIL (bf16 mode; default 192,384; 96 is built and tested but measured no faster than proj GEMM + swin_mlp_fused there).
-        tail_widths = tuple(int(v) for v in os.environ.get("MVLT_BLOCK_TAIL", "192,384").split(",") if v.strip()) \
+        # rows stay in tensor memory between the two halves) for the widths in MVLT_BLOCK_TAIL (bf16 mode; default 96,192,384 — stage 0 runs the persistent
+        # two-tiles-in-flight variant csrc/swin_tail96.cu: 72 us against 140 us for proj GEMM + swin_mlp_fused).
+        tail_widths = tuple(int(v) for v in os.environ.get("MVLT_BLOCK_TAIL", "96,192,384").split(",") if v.strip()) \
             if self.precision == "bf16" else ()
         # norm1 + roll + window_partition + qkv as ONE tcgen05 kernel on CTA pairs (csrc/ln_qkv.cu) for the widths in MVLT_LN_QKV
         lnqkv_widths = tuple(int(v) for v in os.environ.get("MVLT_LN_QKV", "192,384").split(",") if v.strip()) \
