@@ -262,34 +262,29 @@ swin_tail96_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_cons
       }
       tc_fence_after();
       if (q == 0 && i < 8) T96_STAMP(32 + 4 * i + 2);
-      float sum = 0.f;
+      // one pass for both moments, taken about the row's first element (shifted data: no E[x^2] - mean^2 cancellation for rows
+      // whose spread is comparable to their offset — the LayerNorm group is on the critical path of the tile pipeline and a
+      // third sweep over tensor memory cost it 1.2k cycles per tile)
+      float sum = 0.f, sq = 0.f, pivot = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 3; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(acc + c * 32, v);
         tmem_ld_wait();
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-        for (int k = 0; k < 32; k += 4) {
-          s0 += __uint_as_float(v[k]); s1 += __uint_as_float(v[k + 1]); s2 += __uint_as_float(v[k + 2]); s3 += __uint_as_float(v[k + 3]);
-        }
-        sum += (s0 + s1) + (s2 + s3);
-      }
-      const float mean = sum * (1.0f / C);
-      float sq = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 3; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(acc + c * 32, v);
-        tmem_ld_wait();
-        float q0 = 0.f, q1 = 0.f;
+        if (c == 0) pivot = __uint_as_float(v[0]);
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
         for (int k = 0; k < 32; k += 2) {
-          const float d0 = __uint_as_float(v[k]) - mean, d1 = __uint_as_float(v[k + 1]) - mean;
+          const float d0 = __uint_as_float(v[k]) - pivot, d1 = __uint_as_float(v[k + 1]) - pivot;
+          s0 += d0; s1 += d1;
           q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
         }
+        sum += s0 + s1;
         sq += q0 + q1;
       }
+      const float dm = sum * (1.0f / C);                  // mean - pivot
+      const float mean = pivot + dm;
+      sq = fmaxf(sq - sum * dm, 0.f);                     // sum (x - mean)^2
       const float rstd = 1.0f / sqrtf(sq * (1.0f / C) + p.eps);
       uint8_t* a1 = smem + OFF_A1 + s * 32768;
 #pragma unroll 1
