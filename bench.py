@@ -523,8 +523,15 @@ def run_ours(args):
     d_imgs, d_ids = [t.to(dev) for t in imgs], [t.to(dev) for t in idss]
     h_imgs, h_ids = [t.pin_memory() for t in imgs], [t.pin_memory() for t in idss]
 
-    runner = runtime.GraphRunner(lambda im, tx: model(im, tx, None), (d_imgs[0], d_ids[0]), slots=2)
+    # one captured graph per rotated input batch: the device-resident loop replays them in turn with NO copy in the timed region
+    # (the first version refreshed one static input by a 38.5 MB device-to-device copy per step: ~15 us that were not the hot path);
+    # the end-to-end loop reuses slots 0 / 1 as its double buffer
+    runner = runtime.GraphRunner(lambda im, tx: model(im, tx, None), (d_imgs[0], d_ids[0]), slots=n_rot)
     launches = runner.launches_per_replay
+    for i in range(n_rot):
+        runner.static_in[i][0].copy_(d_imgs[i])
+        runner.static_in[i][1].copy_(d_ids[i])
+    e2e_slots = 2
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -535,11 +542,7 @@ def run_ours(args):
     # ---- device-resident throughput: K graph replays between two events on the compute stream
     def resident(k):
         for i in range(k):
-            slot = i % 2
-            with torch.cuda.stream(runner.compute):
-                runner.static_in[slot][0].copy_(d_imgs[i % n_rot], non_blocking=True)   # D2D refresh (38.5 MB) keeps inputs distinct
-                runner.static_in[slot][1].copy_(d_ids[i % n_rot], non_blocking=True)
-            runner.replay(slot)
+            runner.replay(i % n_rot)
 
     resident(args.warmup)
     barrier()
@@ -557,7 +560,7 @@ def run_ours(args):
     def e2e(k):
         pending = []
         for i in range(k):
-            if len(pending) == runner.slots:
+            if len(pending) == e2e_slots:
                 runner.result(pending.pop(0))
             pending.append(runner.submit((h_imgs[i % n_rot], h_ids[i % n_rot])))
         for s in pending:
