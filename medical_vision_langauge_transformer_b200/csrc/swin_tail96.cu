@@ -44,9 +44,9 @@ constexpr int OFF_STG = OFF_A2 + 2 * 16384;      // 4 store warps x one 32x32 fp
 constexpr int OFF_PAR = OFF_STG + 4 * 4096;      // gamma | beta | b_proj | b2 (96 each) | b1 (384)
 constexpr int PAR_FLOATS = 4 * C + HID;
 constexpr int OFF_BAR = OFF_PAR + PAR_FLOATS * 4;
-constexpr int NUM_BARS = 28;
-constexpr int SMEM = OFF_BAR + 256 + 1024;
-static_assert(OFF_A1 % 1024 == 0 && OFF_A2 % 1024 == 0 && OFF_STG % 1024 == 0 && NUM_BARS * 8 + 8 <= 256 && SMEM <= 227 * 1024, "layout");
+constexpr int NUM_BARS = 32;
+constexpr int SMEM = OFF_BAR + 512 + 1024;
+static_assert(OFF_A1 % 1024 == 0 && OFF_A2 % 1024 == 0 && OFF_STG % 1024 == 0 && NUM_BARS * 8 + 8 <= 512 && SMEM <= 227 * 1024, "layout");
 
 struct Params {
   float* x;
@@ -67,7 +67,7 @@ static unsigned long long* g_trace = nullptr;
 
 __global__ void __launch_bounds__(THREADS, 1)
 swin_tail96_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_xs,
-                   const __grid_constant__ CUtensorMap tmap_wp, const __grid_constant__ CUtensorMap tmap_w1,
+                   const __grid_constant__ CUtensorMap tmap_xh, const __grid_constant__ CUtensorMap tmap_wp, const __grid_constant__ CUtensorMap tmap_w1,
                    const __grid_constant__ CUtensorMap tmap_w2, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -86,7 +86,7 @@ swin_tail96_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_cons
   uint64_t* x_done = bars + 15;             // [3] x + b_proj in ACC2[slot]                         (leader, 2 x 4 warps)
   uint64_t* acc2_full = bars + 18;          // [3] last fc2 product of the slot's tile retired      (multicast)
   uint64_t* x_ready = bars + 21;            // [3] this CTA's x rows are in ACC2[slot]              (local, 4 warps; MLP-only mode)
-  uint64_t* x_land = bars + 24;             // [4] one per store-group warp: residual chunk landed in its staging buffer (local)
+  uint64_t* x_land = bars + 24;             // [4][2] per store-group warp and half-buffer: residual half-chunk landed (local)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,7 +96,7 @@ swin_tail96_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_cons
   const bool with_proj = p.with_proj != 0;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_o); tma_prefetch_desc(&tmap_xs); tma_prefetch_desc(&tmap_wp); tma_prefetch_desc(&tmap_w1);
+    tma_prefetch_desc(&tmap_o); tma_prefetch_desc(&tmap_xs); tma_prefetch_desc(&tmap_xh); tma_prefetch_desc(&tmap_wp); tma_prefetch_desc(&tmap_w1);
     tma_prefetch_desc(&tmap_w2);
     mbar_init(w_full, 1);
     for (int s = 0; s < 2; ++s) {
@@ -105,7 +105,7 @@ swin_tail96_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_cons
     }
     mbar_init(acc1_full, 1); mbar_init(acc1_empty, 32);
     for (int s = 0; s < 3; ++s) { mbar_init(&x_done[s], 8); mbar_init(&acc2_full[s], 1); mbar_init(&x_ready[s], 4); }
-    for (int w = 0; w < 4; ++w) mbar_init(&x_land[w], 1);
+    for (int w = 0; w < 8; ++w) mbar_init(&x_land[w], 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -357,40 +357,50 @@ swin_tail96_kernel(const __grid_constant__ CUtensorMap tmap_o, const __grid_cons
     uint8_t* sb = smem + OFF_STG + (warp - SG0) * 4096;
     const uint32_t srow = (uint32_t)lane * 128u, sswz = (uint32_t)lane & 7u;
     pdl_grid_sync();
-    uint64_t* xbar = &x_land[warp - SG0];
-    uint32_t xphase = 0;
-    // x rows of tile i (+ b_proj) -> ACC2[i & 1]: the 32 x 32 fp32 chunks come through this warp's staging buffer by TMA (the
-    // first version read them with per-thread row loads: 32 scattered 16-byte requests per instruction, 7-9k cycles per tile)
+    uint64_t* xbar = &x_land[2 * (warp - SG0)];
+    uint32_t xcnt = 0;                                                    // half-chunks loaded so far by this warp: buffer = xcnt & 1
+    const uint32_t hrow = (uint32_t)lane * 64u, hswz = ((uint32_t)lane >> 1) & 3u;   // 64-byte rows, SWIZZLE_64B
+    // x rows of tile i (+ b_proj) -> ACC2[i % 3]: six 32 x 16 fp32 half-chunks by TMA through the two halves of this warp's
+    // staging buffer, two loads in flight.  (First version: per-thread row loads, 32 scattered 16-byte requests per instruction,
+    // 7-9k cycles per tile; one 32 x 32 chunk at a time through the whole buffer measured the same as this — with 26 warps on four
+    // schedulers this group advances at its issue share, ~7k cycles per tile either way, which the two-tiles-ahead slack absorbs.)
     auto load_x = [&](int i) {
       const int s = i % 3;
       const int row0 = (pair + i * npairs) * 256 + (int)rank * 128 + q * 32;
-      if (lane == 0 && i + 3 < n_my) {                                    // the chunks this warp loads next: into L2 now
-        const int rown = row0 + 3 * npairs * 256;
-        if (rown < p.M)
-          for (int c = 0; c < 3; ++c)
-            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tmap_xs), "r"(c * 32), "r"(rown) : "memory");
-      }
-#pragma unroll 1
-      for (int c = 0; c < 3; ++c) {
-        if (lane == 0) {
-          bulk_wait_read<0>();                                            // an earlier TMA store may still be reading the buffer
-          mbar_arrive_expect_tx(xbar, 4096);
-          tma_load_2d(sb, &tmap_xs, xbar, c * 32, row0);                  // rows past M arrive as zeros
+      auto issue = [&](int hc) {
+        const uint32_t b = (xcnt + hc) & 1;
+        mbar_arrive_expect_tx(&xbar[b], 2048);
+        tma_load_2d(sb + b * 2048, &tmap_xh, &xbar[b], hc * 16, row0);   // rows past M arrive as zeros
+      };
+      if (lane == 0) {
+        if (i + 3 < n_my) {                                               // the chunks this warp loads next: into L2 now
+          const int rown = row0 + 3 * npairs * 256;
+          if (rown < p.M)
+            for (int c = 0; c < 3; ++c)
+              asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tmap_xs), "r"(c * 32), "r"(rown) : "memory");
         }
-        __syncwarp();
-        mbar_wait(xbar, xphase & 1);
-        ++xphase;
-        uint32_t v[32];
+        bulk_wait_read<0>();                                              // the output stores of the tile just drained have left the buffer
+        issue(0);
+        issue(1);
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int hc = 0; hc < 6; ++hc) {
+        const uint32_t n = xcnt + hc, b = n & 1;
+        mbar_wait(&xbar[b], (n >> 1) & 1);
+        uint32_t v[16];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float4 a = *reinterpret_cast<const float4*>(sb + srow + (((uint32_t)k ^ sswz) << 4));
-          const float4 bb = *reinterpret_cast<const float4*>(bp + c * 32 + 4 * k);
+        for (int k = 0; k < 4; ++k) {
+          const float4 a = *reinterpret_cast<const float4*>(sb + b * 2048 + hrow + (((uint32_t)k ^ hswz) << 4));
+          const float4 bb = *reinterpret_cast<const float4*>(bp + hc * 16 + 4 * k);
           v[4 * k] = __float_as_uint(a.x + bb.x); v[4 * k + 1] = __float_as_uint(a.y + bb.y);
           v[4 * k + 2] = __float_as_uint(a.z + bb.z); v[4 * k + 3] = __float_as_uint(a.w + bb.w);
         }
-        __syncwarp();                                                     // every lane has read the chunk before the buffer is refilled
-        tmem_st_32x32(tl + s * 96 + c * 32, v);
+        __syncwarp();                                                     // every lane has read the half-chunk before its buffer is refilled
+        if (lane == 0 && hc + 2 < 6) issue(hc + 2);
+        tmem_st_32x16(tl + s * 96 + hc * 16, v);
       }
+      xcnt += 6;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -480,9 +490,11 @@ int launch_swin_tail96(const void* o, float* x, long long ldx, const void* w_pro
     g_pairs = n;
   }
   const bool with_proj = o != nullptr;
-  CUtensorMap to, txs, twp, tw1, tw2;
+  CUtensorMap to, txs, txh, twp, tw1, tw2;
   if ((rc = make_tmap(&txs, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, M, C, ldx, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_NONE)) != MVLT_OK) return rc;
+  if ((rc = make_tmap(&txh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, M, C, ldx, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) != MVLT_OK) return rc;
   if (with_proj) {
     if ((rc = make_tmap(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, o, M, C, C, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) != MVLT_OK) return rc;
@@ -505,7 +517,7 @@ int launch_swin_tail96(const void* o, float* x, long long ldx, const void* w_pro
   const int pairs = p.tiles < g_pairs ? p.tiles : g_pairs;
   cfg.gridDim = dim3(2 * pairs);
   cfg.numAttrs = mvlt_pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, swin_tail96_kernel, to, txs, twp, tw1, tw2, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, swin_tail96_kernel, to, txs, txh, twp, tw1, tw2, p);
   return e == cudaSuccess ? MVLT_OK : (int)e;
 }
 
