@@ -305,7 +305,7 @@ def _tail_case(M, C, seed):
 
 
 @pytest.mark.parametrize("M,C", [(256, 384), (12544, 384), (300, 384), (37, 384), (1568, 192), (50176, 192), (129, 192), (6272, 96),
-                                 (200704, 96), (77, 96)])
+                                 (200704, 96), (77, 96), (19000, 96), (40000, 96), (57000, 96)])   # C = 96: 1 .. 11 tiles per persistent CTA pair
 @pytest.mark.parametrize("with_proj", [True, False])
 def test_swin_block_tail(cuda, M, C, with_proj):
     """proj + residual + LayerNorm + fc1 + GELU + fc2 + residual in one CTA-pair kernel against (1) a torch restatement with
