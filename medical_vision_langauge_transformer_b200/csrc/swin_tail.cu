@@ -541,8 +541,8 @@ extern "C" int mvlt_swin_block_tail(const void* o, float* x, long long ldx, cons
   p.trace = g_tail_trace;
   if (C == 96) {
     // stage 0: the persistent two-tiles-in-flight kernel (swin_tail96.cu); MVLT_TAIL96=0 keeps the one-tile-per-pair kernel
-    static int persistent = -1;
-    if (persistent < 0) { const char* e = getenv("MVLT_TAIL96"); persistent = (e && atoi(e) == 0) ? 0 : 1; }
+    const char* e = getenv("MVLT_TAIL96");           // read per call: the tests run both kernels in one process
+    const bool persistent = !(e && atoi(e) == 0);
     if (persistent) return launch_swin_tail96(o, x, ldx, w_proj, b_proj, gamma, beta, eps, w1, b1, w2, b2, M, stream);
     return launch_swin_tail<96>(p, o, x, ldx, o ? w_proj : nullptr, w1, w2, stream);
   }

@@ -333,6 +333,21 @@ def test_swin_block_tail(cuda, M, C, with_proj):
     assert torch.equal(xf, xf2), "run-to-run bit reproducibility"
 
 
+@pytest.mark.parametrize("M", [300, 57000])
+def test_swin_block_tail_c96_both_kernels_agree(cuda, monkeypatch, M):
+    """Stage 0 has two block-tail kernels: the persistent three-tiles-in-flight one (default) and the one-tile-per-pair one
+    (MVLT_TAIL96=0).  Same arithmetic except for the LayerNorm statistics (one shifted sweep vs two passes): fp32 results agree
+    to rounding."""
+    from medical_vision_langauge_transformer_b200 import ops
+    x, o, wp, bp, g, b, w1, b1, w2, b2 = _tail_case(M, 96, 11)
+    xa, xb = x.clone(), x.clone()
+    ops.swin_block_tail(xa, o, wp, bp, g, b, 1e-5, w1, b1, w2, b2)
+    monkeypatch.setenv("MVLT_TAIL96", "0")
+    ops.swin_block_tail(xb, o, wp, bp, g, b, 1e-5, w1, b1, w2, b2)
+    assert relerr(xa, xb) < 2e-3, relerr(xa, xb)                           # bf16 roundings of LayerNorm rows that differ in the last fp32 bit
+    assert not torch.equal(xa, x)
+
+
 @pytest.mark.parametrize("B,H,C,shift", [(2, 14, 384, 0), (2, 14, 384, 3), (64, 14, 384, 3), (3, 28, 192, 3), (64, 28, 192, 0), (1, 14, 384, 3),
                                            (1, 56, 96, 0), (2, 56, 96, 3), (64, 56, 96, 3)])
 def test_swin_ln_qkv(cuda, B, H, C, shift):
