@@ -6,7 +6,10 @@ What is here: every dgrad (dX = dY . W) and wgrad (dW = dY^T . X) of the layer's
 transposes are CUDA kernels of csrc/backward.cu.  bf16 operands, fp32 accumulation, fp32 residual-stream gradients — the mixed
 precision of the forward.  Parity: tests/test_backward_gpu.py against torch.autograd of the oracle's `bert_layer`.
 
-What is NOT here: the other layers' chaining, the Swin backward, dropout / DropPath in train mode, the optimizer, the
+`bert_encoder_forward / bert_encoder_backward` chain the layers (HF modeling_bert.py:424-453 BertEncoder) and return the gradients under
+the reference's `encoder.layer.{l}.…` keys.
+
+What is NOT here: the embedding / pooler / head backward, the Swin backward, dropout / DropPath in train mode, the optimizer, the
 gradient all-reduce, and tensor-core versions of the attention / row backward kernels.  The forward below uses the unfused kernel chain
 because it has to keep the pre-LayerNorm sums and the pre-GELU activation that the fused inference kernels never write."""
 from __future__ import annotations
@@ -93,3 +96,31 @@ def bert_layer_backward(w, saved: dict, dout: torch.Tensor) -> Tuple[torch.Tenso
         g[f"attention.self.{name}.bias"] = dbqkv[i * D:(i + 1) * D]
     dh = ops.linear(dqkv, w["qkv_t"], residual=ds1, out_dtype=torch.float32)                   # + the residual branch of s1
     return dh, g
+
+
+def pack_encoder(sd: Dict[str, torch.Tensor], prefix: str = "MVLBert.encoder.layer.", n_layers: int = 12, device="cuda"):
+    """Kernel-layout copies of every encoder layer (reference keys `{prefix}{l}.…`)."""
+    return [pack_layer(sd, f"{prefix}{l}.", device) for l in range(n_layers)]
+
+
+def bert_encoder_forward(ws, h: torch.Tensor, kmask: Optional[torch.Tensor], B: int, S: int, heads: int = 12, seq2seq: bool = False,
+                         obj_end: int = 50, eps: float = 1e-12):
+    """The post-LN layer stack on h (fp32 [B*S, D]) -> (last hidden state fp32, per-layer saved activations)."""
+    saved = []
+    for w in ws:
+        h, sv = bert_layer_forward(w, h, kmask, B, S, heads, seq2seq, obj_end, eps)
+        saved.append(sv)
+    return h, saved
+
+
+def bert_encoder_backward(ws, saved, dout: torch.Tensor):
+    """-> (dh of the encoder input, {`{l}.{parameter key}`: gradient}) — layers walked in reverse, each layer's saved activations
+    released as soon as its gradients are formed."""
+    grads: Dict[str, torch.Tensor] = {}
+    d = dout
+    for l in range(len(ws) - 1, -1, -1):
+        d, g = bert_layer_backward(ws[l], saved[l], d)
+        saved[l] = None
+        for k, v in g.items():
+            grads[f"{l}.{k}"] = v
+    return d, grads

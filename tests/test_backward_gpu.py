@@ -122,3 +122,42 @@ def test_bert_layer_backward_vs_oracle_autograd(cuda, B, L, seq2seq):
     assert max(worst.values()) < 2e-2, worst
     dh2, grads2 = training.bert_layer_backward(w, saved, dout.view(B * S, D).cuda())
     assert torch.equal(dh, dh2) and all(torch.equal(grads[k], grads2[k]) for k in grads)      # deterministic
+
+
+@pytest.mark.parametrize("n_layers,B,L", [(3, 2, 80), (12, 2, 23)])
+def test_bert_encoder_backward_vs_oracle_autograd(cuda, n_layers, B, L):
+    """The layer stack chained (HF:424-453): dh of the encoder input and every layer's 16 parameter gradients against fp32 autograd of
+    the oracle's layers on the host.  Errors of the bf16 backward compound through the depth: bar 3e-2 of each gradient's max-abs."""
+    from medical_vision_langauge_transformer_b200 import synth, training
+    from medical_vision_langauge_transformer_b200.modules import config as C, model as M
+    from oracle import mvlt_oracle as O
+    model = M.MVLBertForVQA(C.offline_config("vqa", max_length=L)).eval()
+    sd = {k: v.clone() for k, v in synth.load_synth(model, 0, "stress").items()}
+    n_obj, D = 49, 768
+    S = n_obj + 2 + L
+    ids = synth.synth_token_ids(B, L, 5)
+    h = rnd(B, S, D, seed=21)
+    dout = rnd(B, S, D, seed=22, scale=0.1)
+    mask = O.joint_attention_mask(ids, n_obj, False)
+    prefix = "MVLBert.encoder.layer."
+    params = {f"{l}.{k}": sd[f"{prefix}{l}.{k}"].clone().requires_grad_(True) for l in range(n_layers) for k in training.LAYER_PARAM_KEYS}
+    href = h.clone().requires_grad_(True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    x = href
+    for l in range(n_layers):
+        x = O.bert_layer({f"{prefix}{l}.{k}": params[f"{l}.{k}"] for k in training.LAYER_PARAM_KEYS}, f"{prefix}{l}.", x, mask)
+    x.backward(dout)
+    ws = training.pack_encoder(sd, prefix, n_layers)
+    out, saved = training.bert_encoder_forward(ws, h.view(B * S, D).cuda(), mask.view(B, S).cuda().contiguous(), B, S, 12, False, n_obj + 1)
+    assert relerr(out, x.detach().view(B * S, D)) < 1e-2
+    dh, grads = training.bert_encoder_backward(ws, saved, dout.view(B * S, D).cuda())
+    assert set(grads) == set(params) and all(sv is None for sv in saved)
+    worst = {"dh": relerr(dh, href.grad.view(B * S, D))}
+    for k in params:
+        if k.endswith("attention.self.key.bias"):          # identically zero in exact arithmetic: measured on the query-bias scale
+            qb = params[k.replace("key", "query")].grad.abs().max()
+            worst[k] = ((grads[k].cpu() - params[k].grad).abs().max() / qb).item()
+        else:
+            worst[k] = relerr(grads[k], params[k].grad)
+    print(f"{n_layers} layers, B={B}, L={L}: worst relerr {max(worst.values()):.2e} ({max(worst, key=worst.get)})")
+    assert max(worst.values()) < 3e-2, {k: v for k, v in worst.items() if v > 1e-2}
